@@ -1,0 +1,153 @@
+"""Generate golden fixtures by running the LIVE reference (build container only).
+
+Usage (from the repo root, in the build container where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+Imports the reference's hot-path modules through the shim documented in
+SURVEY.md (appendix) -- the package's ``__init__`` needs xarray, the three
+modules below only need numpy/scipy -- runs them on seeded inputs and writes
+``tests/golden/*.npz``.  The fixtures travel to the GPU box; the reference does
+not.  Nothing here is imported by the product.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = os.environ.get("SC_REFERENCE_PATH", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_reference():
+    pkg = types.ModuleType("spectral_connectivity")
+    pkg.__path__ = [os.path.join(REF, "spectral_connectivity")]
+    sys.modules["spectral_connectivity"] = pkg
+    import spectral_connectivity.connectivity as C
+    import spectral_connectivity.minimum_phase_decomposition as M
+    import spectral_connectivity.transforms as T
+    return T, C, M
+
+
+def series(seed, n, t, s, fs):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle.oracle import synthetic_series
+    return synthetic_series(n, t, s, fs, seed)
+
+
+def main():
+    T, C, M = load_reference()
+    np.random.seed(42)
+
+    # ---- 1. index arithmetic (bit exact) ---------------------------------
+    rows = []
+    cases = [
+        (1000, 500.0, None, None), (10_000, 1000.0, 1.0, None), (10_000, 1000.0, 1.0, 0.5),
+        (120_000 // 50, 2000.0, 0.060, None), (120_000 // 50, 2000.0, 0.060, 0.030),
+        (5000, 1000.0, 0.3, 0.1), (5000, 1500.0, 0.1234, 0.0371), (4097, 256.0, 1.001, 0.333),
+        (3000, 1000.0 / 3.0, 0.75, 0.3), (777, 123.0, 0.5, 0.07), (2048, 1024.0, 0.0625, 0.03125),
+    ]
+    geom = {}
+    for ci, (n, fs, dur, step) in enumerate(cases):
+        m = T.Multitaper(np.zeros((n, 1, 1)), sampling_frequency=fs, time_window_duration=dur,
+                         time_window_step=step, time_halfbandwidth_product=2)
+        rows.append([n, fs, -1 if dur is None else dur, -1 if step is None else step,
+                     m.n_time_samples_per_window, m.n_time_samples_per_step, m.n_fft_samples,
+                     len(m.time), m.n_tapers])
+        geom[f"time_{ci}"] = np.asarray(m.time)
+        geom[f"freq_{ci}"] = np.asarray(m.frequencies)
+    np.savez_compressed(os.path.join(HERE, "geometry.npz"), table=np.array(rows, dtype=float), **geom)
+
+    # ---- 2. tapers --------------------------------------------------------
+    tap = {}
+    for n, nw, k in [(64, 2.0, 3), (120, 5.0, 9), (1000, 3.0, 5), (1000, 4.0, 7), (257, 2.5, 4),
+                     (50, 1.0, 1), (80, 2.0, 3)]:
+        t_, ev = T.dpss_windows(n, nw, k, is_low_bias=False)
+        tap[f"tapers_{n}_{nw}_{k}"] = np.asarray(t_)
+        tap[f"eig_{n}_{nw}_{k}"] = np.asarray(ev)
+    # a case where the low-bias filter drops tapers
+    t_, ev = T.dpss_windows(64, 1.5, 4, is_low_bias=True)
+    tap["lowbias_64_1.5_4"] = np.asarray(t_)
+    np.savez_compressed(os.path.join(HERE, "tapers.npz"), **tap)
+
+    # ---- 3. Multitaper.fft -------------------------------------------------
+    mt = {}
+    mt_cases = {
+        "whole": dict(n=256, t=2, s=3, fs=200.0, kw=dict(time_halfbandwidth_product=2)),
+        "sliding": dict(n=400, t=3, s=4, fs=200.0,
+                        kw=dict(time_halfbandwidth_product=2, time_window_duration=0.4,
+                                time_window_step=0.2)),
+        "linear": dict(n=300, t=2, s=2, fs=100.0,
+                       kw=dict(time_halfbandwidth_product=3, time_window_duration=1.0,
+                               detrend_type="linear")),
+        "nodetrend": dict(n=300, t=2, s=2, fs=100.0,
+                          kw=dict(time_halfbandwidth_product=3, time_window_duration=1.0,
+                                  detrend_type=None)),
+        "crop": dict(n=200, t=2, s=3, fs=100.0,
+                     kw=dict(time_halfbandwidth_product=2, time_window_duration=1.0,
+                             n_fft_samples=64)),
+        "pad": dict(n=200, t=2, s=3, fs=100.0,
+                    kw=dict(time_halfbandwidth_product=2, time_window_duration=1.0,
+                            n_fft_samples=128)),
+        "odd": dict(n=189, t=2, s=5, fs=63.0,
+                    kw=dict(time_halfbandwidth_product=2, time_window_duration=1.0)),
+        "prime": dict(n=202, t=1, s=2, fs=101.0,
+                      kw=dict(time_halfbandwidth_product=2, time_window_duration=1.0,
+                              n_fft_samples=101)),
+    }
+    for name, c in mt_cases.items():
+        x = series(100 + len(mt), c["n"], c["t"], c["s"], c["fs"])
+        m = T.Multitaper(x, sampling_frequency=c["fs"], **c["kw"])
+        mt[f"{name}_x"] = x
+        mt[f"{name}_fft"] = np.asarray(m.fft())
+        mt[f"{name}_tapers"] = np.asarray(m.tapers)
+        mt[f"{name}_meta"] = np.array([m.n_time_samples_per_window, m.n_time_samples_per_step,
+                                       m.n_fft_samples, c["fs"]], dtype=float)
+    np.savez_compressed(os.path.join(HERE, "multitaper_fft.npz"), **mt)
+
+    # ---- 4. connectivity measures -----------------------------------------
+    conn = {}
+    x = series(7, 300, 4, 4, 100.0)
+    m = T.Multitaper(x, sampling_frequency=100.0, time_halfbandwidth_product=3,
+                     time_window_duration=1.0)
+    coef = np.asarray(m.fft())
+    conn["x"] = x
+    conn["coef"] = coef
+    conn["meta"] = np.array([100.0, 3.0, 1.0])
+    methods = ["power", "coherency", "coherence_magnitude", "coherence_phase",
+               "imaginary_coherence", "phase_locking_value", "phase_lag_index",
+               "weighted_phase_lag_index", "debiased_squared_phase_lag_index",
+               "debiased_squared_weighted_phase_lag_index", "pairwise_phase_consistency",
+               "pairwise_spectral_granger_prediction"]
+    for et in ["trials_tapers", "trials", "tapers", "time", "time_trials", "time_tapers",
+               "time_trials_tapers"]:
+        c = C.Connectivity(coef, expectation_type=et, frequencies=m.frequencies, time=m.time)
+        conn[f"{et}__csm"] = np.asarray(c._expectation_cross_spectral_matrix())
+        for meth in methods:
+            if meth == "pairwise_spectral_granger_prediction" and et != "trials_tapers":
+                continue
+            conn[f"{et}__{meth}"] = np.asarray(getattr(c, meth)())
+    np.savez_compressed(os.path.join(HERE, "connectivity.npz"), **conn)
+
+    # ---- 5. Wilson ----------------------------------------------------------
+    wil = {}
+    c = C.Connectivity(coef, frequencies=m.frequencies, time=m.time)
+    csm = np.asarray(c._expectation_cross_spectral_matrix())
+    sub = csm[..., np.array([[0], [1]]), np.array([[0, 1]])]
+    wil["csm2"] = sub
+    wil["g2"] = np.asarray(M.minimum_phase_decomposition(sub))
+    sub3 = csm[..., np.array([[0], [2], [3]]), np.array([[0, 2, 3]])]
+    wil["csm3"] = sub3
+    wil["g3"] = np.asarray(M.minimum_phase_decomposition(sub3))
+    wil["csm4"] = csm
+    wil["g4"] = np.asarray(M.minimum_phase_decomposition(csm))
+    np.savez_compressed(os.path.join(HERE, "wilson.npz"), **wil)
+    print("golden fixtures written to", HERE)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,116 @@
+"""Pins the oracle: NumPy restatement vs fixtures generated from the live
+reference (tests/golden/make_golden.py) and the reference's own known answers."""
+import numpy as np
+import pytest
+from conftest import assert_parity, golden
+
+from oracle import oracle as O
+
+TIGHT = 1e-9
+
+
+def test_geometry_bit_exact():
+    g = golden("geometry.npz")
+    for ci, row in enumerate(g["table"]):
+        n_samples, fs, dur, step = int(row[0]), row[1], row[2], row[3]
+        n, st, nfft = O.window_geometry(n_samples, fs, None if dur < 0 else dur,
+                                        None if step < 0 else step)
+        assert (n, st, nfft) == (int(row[4]), int(row[5]), int(row[6]))
+        assert O.n_windows(n_samples, n, st) == int(row[7])
+        assert O.default_n_tapers(2) == int(row[8])
+        assert np.array_equal(O.window_times(n_samples, fs, n, st), g[f"time_{ci}"])
+        assert np.array_equal(O.frequencies(nfft, fs), g[f"freq_{ci}"])
+
+
+def test_sliding_window_known_answers():
+    # reference tests/test_transforms.py:39-59
+    a = np.arange(1, 6, dtype=float)[:, None, None]
+    assert np.array_equal(O.sliding_windows(a, 3, 1)[:, 0, 0], [[1, 2, 3], [2, 3, 4], [3, 4, 5]])
+    assert np.array_equal(O.sliding_windows(a, 3, 2)[:, 0, 0], [[1, 2, 3], [3, 4, 5]])
+
+
+def test_tapers():
+    g = golden("tapers.npz")
+    for key in g.files:
+        if not key.startswith("tapers_"):
+            continue
+        _, n, nw, k = key.split("_")
+        got = O.dpss_tapers(int(n), float(nw), int(k), fs=1.0, is_low_bias=False).T
+        assert_parity(got, g[key], 1e-9, key)
+    got = O.dpss_tapers(64, 1.5, 4, fs=1.0, is_low_bias=True).T
+    assert_parity(got, g["lowbias_64_1.5_4"], 1e-9, "lowbias")
+
+
+@pytest.mark.parametrize("name", ["whole", "sliding", "linear", "nodetrend", "crop", "pad", "odd",
+                                  "prime"])
+def test_multitaper_fft(name):
+    g = golden("multitaper_fft.npz")
+    n, step, nfft, fs = g[f"{name}_meta"]
+    dt = {"linear": "linear", "nodetrend": None}.get(name, "constant")
+    got = O.multitaper_fft(g[f"{name}_x"], fs, g[f"{name}_tapers"], int(n), int(step), int(nfft), dt)
+    assert_parity(got, g[f"{name}_fft"], TIGHT, name)
+
+
+MEASURES = {
+    "power": lambda c, et: O._nonneg(O.power(c, et), -2),
+    "coherency": O.coherency,
+    "coherence_magnitude": O.coherence_magnitude,
+    "coherence_phase": O.coherence_phase,
+    "imaginary_coherence": O.imaginary_coherence,
+    "phase_locking_value": O.phase_locking_value,
+    "phase_lag_index": O.phase_lag_index,
+    "weighted_phase_lag_index": O.weighted_phase_lag_index,
+    "debiased_squared_phase_lag_index": O.debiased_squared_phase_lag_index,
+    "debiased_squared_weighted_phase_lag_index": O.debiased_squared_weighted_phase_lag_index,
+    "pairwise_phase_consistency": O.pairwise_phase_consistency,
+}
+
+
+@pytest.mark.parametrize("et", list(O.EXPECTATION_AXES))
+def test_measures(et):
+    g = golden("connectivity.npz")
+    coef = g["coef"]
+    assert_parity(O.expected_csm(coef, et), g[f"{et}__csm"], TIGHT, "csm")
+    assert_parity(O.expected_csm(coef, et, row_block=3), g[f"{et}__csm"], TIGHT, "csm blocked")
+    for name, fn in MEASURES.items():
+        tol = 1e-6 if name == "coherence_phase" else TIGHT
+        assert_parity(fn(coef, et), g[f"{et}__{name}"], tol, f"{et}/{name}")
+
+
+def test_granger():
+    g = golden("connectivity.npz")
+    coef = g["coef"]
+    csm = O.expected_csm(coef)
+    got = O.pairwise_granger(csm, O.power(coef))
+    assert_parity(got, g["trials_tapers__pairwise_spectral_granger_prediction"], 1e-8, "granger")
+
+
+@pytest.mark.parametrize("s", [2, 3, 4])
+def test_wilson(s):
+    g = golden("wilson.npz")
+    got = O.wilson(g[f"csm{s}"])
+    assert_parity(got, g[f"g{s}"], 1e-9, f"wilson{s}")
+
+
+def test_wilson_reference_known_answers():
+    # reference tests/test_minimum_phase_decomposition.py:44-56 and :96-119
+    from scipy.signal import freqz_zpk
+    csm = np.ones((3, 11, 2, 2), dtype=complex) * 4
+    csm[..., 1, 0] = 0
+    g0 = O.wilson_initial(csm)
+    assert np.allclose(g0, np.eye(2) * 2)
+    _, h1 = freqz_zpk(0.25, 0.50, 1.00, whole=True)
+    _, h2 = freqz_zpk(0.125, 0.25, 1.00, whole=True)
+    expected = np.zeros((2, h1.shape[0], 1, 1), dtype=complex)
+    expected[0, :, 0, 0] = h1
+    expected[1, :, 0, 0] = h2
+    s = expected @ np.conj(np.swapaxes(expected, -1, -2))
+    assert np.allclose(O.wilson(s), expected)
+
+
+def test_csm_known_answer():
+    # reference tests/test_connectivity.py:25-56, :82-99
+    coef = np.zeros((1, 1, 1, 1, 2), dtype=complex)
+    coef[..., :] = [2 * np.exp(1j * np.pi / 2), 3 * np.exp(-1j * np.pi / 2)]
+    assert np.allclose(O.cross_spectral_matrix(coef)[0, 0, 0, 0], [[4, -6], [-6, 9]])
+    assert np.allclose(O.power(coef)[0, 0], [4, 9])
