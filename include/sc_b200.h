@@ -1,0 +1,147 @@
+/* sc_b200.h -- C ABI of the B200-native multitaper spectral-connectivity hot path.
+ *
+ * The reference (Eden-Kramer-Lab/spectral_connectivity, pure Python) has no FFI;
+ * its only backend seam is the module-level ``xp`` alias chosen at import time
+ * (transforms.py:405-439, connectivity.py:31-65, minimum_phase_decomposition.py:14-26).
+ * Each entry point below replaces the NumPy/SciPy (or CuPy) call sequence of one
+ * reference function; the file:line of what it replaces is cited per function.
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless it says "host"; the caller owns all
+ *    memory (inputs, outputs, workspaces); the library never allocates or frees;
+ *  - all work is enqueued asynchronously on ``stream`` (a cudaStream_t passed as void*);
+ *  - return value 0 = success, negative = error (SC_ERR_*); sc_last_error() gives the
+ *    message of the last failure on the calling thread;
+ *  - "planar coefficients" Xp: float32 [B][F][2][R][S] -- B kept (batch) index,
+ *    F frequency bins, plane 0 = real / 1 = imaginary, R reduced (observation) index,
+ *    S signals (fastest).  (B, R) are built from (window, trial, taper) by the linear
+ *    map  b = w*map[0] + t*map[1] + k*map[2],  r = w*map[3] + t*map[4] + k*map[5],
+ *    which expresses all seven ``expectation_type``s of connectivity.py:67-75;
+ *  - complex outputs are interleaved (re, im) float32 ("c64") or float64 ("c128").
+ */
+#ifndef SC_B200_H
+#define SC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_OK 0
+#define SC_ERR_INVALID_ARGUMENT (-1)
+#define SC_ERR_UNSUPPORTED (-2)
+#define SC_ERR_WORKSPACE (-3)
+#define SC_ERR_CUDA (-4)
+
+/* detrend modes of Multitaper(detrend_type=...) -- transforms.py:1798-1915 */
+#define SC_DETREND_NONE 0
+#define SC_DETREND_CONSTANT 1
+#define SC_DETREND_LINEAR 2
+
+/* sc_mt_fft output layouts */
+#define SC_LAYOUT_PLANAR 0    /* float32 [B][F][2][R][S], see above                         */
+#define SC_LAYOUT_REFERENCE 1 /* c64 (W,T,K,F,S): the logical layout of Multitaper.fft()  */
+
+/* sc_csm modes: what is accumulated over the R observations of each (b, f, i, j) */
+#define SC_CSM_CROSS 0 /* sum x_i conj(x_j)                        -> c64 [B][F][S][S]      */
+#define SC_CSM_PLV 1   /* sum x_i conj(x_j)/|x_i conj(x_j)|        -> c64 [B][F][S][S]      */
+#define SC_CSM_PLI 2   /* 4 real planes [4][B][F][S][S]: sum sign(Im), sum |Im|,
+                          sum Im^2, sum Im (diagonal Im forced to 0)                       */
+
+/* sc_pairwise_epilogue measures */
+#define SC_M_COHERENCY 0       /* in0 = csm c64, in1 = power -> c64, NaN diagonal           */
+#define SC_M_COHERENCE_MAG 1   /* -> f32 |coherency|^2 clipped to [0,1], NaN diagonal       */
+#define SC_M_COHERENCE_PHASE 2 /* -> f32 angle(coherency), NaN diagonal                     */
+#define SC_M_IMAG_COHERENCE 3  /* -> f32 |Im csm|/norm clipped to [0,1]                     */
+#define SC_M_PLV 4             /* in0 = E[x/|x|] c64 -> f32 magnitude                       */
+#define SC_M_PPC 5             /* in0 = E[x/|x|] c64 -> f32 pairwise phase consistency      */
+#define SC_M_PLI 6             /* in0 = PLI planes (means) -> f32 E[sign Im]                */
+#define SC_M_WPLI 7            /* -> f32 E[Im]/E[|Im|] (weights < eps -> 1)                 */
+#define SC_M_DPLI2 8           /* -> f32 debiased squared PLI                               */
+#define SC_M_DWPLI2 9          /* -> f32 debiased squared wPLI (zero weights -> NaN)        */
+
+/* Wilson / Granger per-problem status flags */
+#define SC_FLAG_NOT_CONVERGED 1 /* max_iterations reached (minimum_phase_decomposition.py:318-322) */
+#define SC_FLAG_NOT_SPD 2       /* lag-0 covariance not positive definite (:78-82); output NaN      */
+
+int sc_version(void);
+const char* sc_last_error(void);
+
+/* Multitaper.fft() -- transforms.py:1147-1171: sliding-window gather (:1311-1374),
+ * detrend (:1798-1915), DPSS taper product + FFT(n=nfft)/fs (:1377-1405), fused.
+ *  x        float32 (N,T,S), S fastest
+ *  tapers   float32 [K][n], already multiplied by sqrt(fs) (transforms.py:1440)
+ *  windows  w0 .. w0+W-1 of the series (window w starts at sample w*step) are transformed;
+ *           they are written at output window index w_out0 + (w - w0)
+ *  nfft     FFT length: zero-pads (nfft > n) or crops (nfft < n) like scipy.fft.fft(n=)
+ *  scale    multiplies the result (1/fs in the reference, :1405)
+ *  twiddle  c64 [nfft], exp(-2 pi i q/nfft)
+ *  layout   SC_LAYOUT_PLANAR: out float32 [B][n_freq_out][2][n_reduce][S] via map[6]
+ *           SC_LAYOUT_REFERENCE: out c64 (W_total?,T,K,n_freq_out,S) indexed by output window
+ *  n_freq_out  number of leading bins written (nfft//2+1 or nfft)
+ *  workspace   only for windows too long for shared memory: sc_mt_fft_workspace_bytes()
+ */
+int sc_mt_fft(const float* x, int64_t N, int64_t T, int64_t S, const float* tapers, int n, int K, int step,
+              int64_t w0, int64_t W, int64_t w_out0, int nfft, int detrend, float scale, const void* twiddle,
+              int layout, int n_freq_out, const int64_t* map /* host [6] */, int64_t n_reduce, void* out,
+              void* workspace, int64_t workspace_bytes, void* stream);
+int64_t sc_mt_fft_workspace_bytes(int n, int nfft);
+
+/* Connectivity(fourier_coefficients=...) boundary -- connectivity.py:277-364: re-lays a
+ * (W,T,K,Nfft,S) c64 array (the Multitaper.fft() layout) into planar coefficients,
+ * keeping the first n_freq_out bins. */
+int sc_repack_coefficients(const void* coef_c64, int64_t W, int64_t T, int64_t K, int64_t nfft, int64_t S,
+                           int n_freq_out, const int64_t* map /* host [6] */, int64_t n_reduce, float* out,
+                           void* stream);
+
+/* Connectivity._power -- connectivity.py:441-445: out[b][f][s] = scale * sum_r |X|^2 */
+int sc_power(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, float scale, float* out, void* stream);
+
+/* Connectivity._expectation_cross_spectral_matrix(fcn) -- connectivity.py:463-526 with
+ * _cross_spectral_matrix (:447-461) / _complex_inner_product (:1799-1822) fused in, and the
+ * per-observation fcn of PLV (:899-903) and the PLI family (:970-980, :1010-1028, :1090-1127).
+ * Results are multiplied by ``scale`` (1/n_observations for the expectation). */
+int sc_csm(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, float scale, int mode, void* out,
+           void* stream);
+
+/* Same contract as sc_csm, always the SIMT fp32 kernel (sc_csm dispatches SC_CSM_CROSS to the
+ * tcgen05 tensor-core kernel when the shape qualifies); kept public so tests can cross-check. */
+int sc_csm_simt(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, float scale, int mode, void* out,
+                void* stream);
+
+/* coherency / coherence_magnitude / coherence_phase / imaginary_coherence (connectivity.py:632-743),
+ * phase_locking_value / pairwise_phase_consistency (:905-931, :1129-1159), phase_lag_index,
+ * weighted / debiased variants (:933-1127): element-wise epilogues on [B][F][S][S]. */
+int sc_pairwise_epilogue(int measure, const void* in0, const float* in1, int64_t B, int64_t F, int64_t S,
+                         double n_observations, void* out, void* stream);
+
+/* minimum_phase_decomposition(csm, tolerance, max_iterations) -- minimum_phase_decomposition.py:227-322
+ * for 2x2 matrices: csm c128 [B][nfft][2][2] two-sided -> G c128 same shape.  Each b is an
+ * independent unit of convergence (frozen at its first iterate with max|dG| < tol, :310-315).
+ *  twiddle  c128 [nfft];  iters/flags int32 [B] (may be NULL). */
+int sc_wilson2(const void* csm_c128, int64_t B, int nfft, double tolerance, int max_iterations,
+               const void* twiddle, void* out_g_c128, int* out_iters, int* out_flags, void* workspace,
+               int64_t workspace_bytes, void* stream);
+
+/* pairwise_spectral_granger_prediction / subset_... -- connectivity.py:1161-1213, 2282-2340 with
+ * _estimate_transfer_function (:1712-1748), _estimate_noise_covariance (:1679-1709),
+ * _remove_instantaneous_causality (:1825-1848), _estimate_predictive_power (:1751-1779) fused.
+ *  csm      c64 [B][F][S][S]; power f32 [B][F][S]
+ *  F        nfft (two-sided spectrum) or nfft/2+1 with hermitian_half=1 (real time series:
+ *           S(-f) = conj S(f), the from_multitaper path)
+ *  pairs    int32 [n_pairs][2] or NULL for all i<j (then n_pairs is ignored)
+ *  out_gc   f32 [B][nfft/2+1][S][S]; entries of processed pairs are overwritten ([i][j] =
+ *           influence j -> i); the caller pre-fills the rest (NaN, connectivity.py:2310, 2336-2338)
+ *  out_iters/out_flags  int32 [n_pairs][B] or NULL */
+int sc_granger_pairwise(const void* csm_c64, const float* power, int64_t B, int F, int nfft, int hermitian_half,
+                        int64_t S, const int* pairs, int64_t n_pairs, double tolerance, int max_iterations,
+                        const void* twiddle_c128, float* out_gc, int* out_iters, int* out_flags,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+int64_t sc_wilson_workspace_bytes(int nfft);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SC_B200_H */

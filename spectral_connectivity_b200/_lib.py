@@ -1,0 +1,88 @@
+"""ctypes binding of libsc_b200.so (the C ABI declared in include/sc_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing the import of any compute
+entry point fails loudly with build instructions.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsc_b200.so")
+
+# symbol -> (restype, argtypes); must list every function of include/sc_b200.h
+_P = c_void_p
+SIGNATURES = {
+    "sc_version": (c_int, []),
+    "sc_last_error": (c_char_p, []),
+    "sc_mt_fft": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64,
+                          c_int, c_int, c_float, _P, c_int, c_int, ctypes.POINTER(c_int64), c_int64, _P, _P,
+                          c_int64, _P]),
+    "sc_mt_fft_workspace_bytes": (c_int64, [c_int, c_int]),
+    "sc_repack_coefficients": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
+                                       ctypes.POINTER(c_int64), c_int64, _P, _P]),
+    "sc_power": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_float, _P, _P]),
+    "sc_csm": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_float, c_int, _P, _P]),
+    "sc_csm_simt": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_float, c_int, _P, _P]),
+    "sc_pairwise_epilogue": (c_int, [c_int, _P, _P, c_int64, c_int64, c_int64, c_double, _P, _P]),
+    "sc_wilson2": (c_int, [_P, c_int64, c_int, c_double, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
+    "sc_granger_pairwise": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int64, _P, c_int64, c_double, c_int,
+                                    _P, _P, _P, _P, _P, c_int64, _P]),
+    "sc_wilson_workspace_bytes": (c_int64, [c_int]),
+}
+
+# constants of include/sc_b200.h
+DETREND = {None: 0, "constant": 1, "c": 1, "linear": 2, "l": 2}
+LAYOUT_PLANAR, LAYOUT_REFERENCE = 0, 1
+CSM_CROSS, CSM_PLV, CSM_PLI = 0, 1, 2
+M_COHERENCY, M_COHERENCE_MAG, M_COHERENCE_PHASE, M_IMAG_COHERENCE = 0, 1, 2, 3
+M_PLV, M_PPC, M_PLI, M_WPLI, M_DPLI2, M_DWPLI2 = 4, 5, 6, 7, 8, 9
+FLAG_NOT_CONVERGED, FLAG_NOT_SPD = 1, 2
+
+_lib = None
+
+
+class NativeLibraryError(ImportError):
+    pass
+
+
+def load():
+    """Load libsc_b200.so once; raise NativeLibraryError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found. The B200 CUDA library is required (no CPU fallback). "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C spectral_connectivity_b200/csrc`.")
+    import torch  # noqa: F401  (loads libcudart.so.12 that the library links against)
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().sc_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def map6(values):
+    return (c_int64 * 6)(*[int(v) for v in values])

@@ -1,0 +1,501 @@
+"""``Connectivity``: drop-in for the reference's connectivity-measure class, B200 backend.
+
+Mirrors ``spectral_connectivity.connectivity.Connectivity`` (connectivity.py:163-1650) for
+the hot path: cross-spectral matrix + expectation (:441-526), power / coherency / coherence
+magnitude & phase / imaginary coherence (:612-743), phase-locking value, pairwise phase
+consistency, phase-lag index and its weighted / debiased variants (:897-1159), and pairwise
+spectral Granger prediction through Wilson factorisation (:1161-1213, :2282-2340).
+
+Differences from the reference that a user can see, all deliberate:
+  * the un-averaged (W,T,K,F,S,S) tensor is never materialised, so ``blocks`` is accepted
+    and ignored; ``dtype`` is accepted, the device pipeline computes in fp32 (complex64)
+    for the spectra/CSM and fp64 for Wilson/Granger;
+  * one streaming pass over window chunks can produce several measures (``compute``);
+  * results are float32 (complex64) NumPy arrays, or CUDA tensors with ``output="torch"``.
+"""
+from __future__ import annotations
+
+import warnings
+from itertools import combinations
+from logging import getLogger
+
+import numpy as np
+import torch
+
+from . import _lib
+from .transforms import EXPECTATION_AXES, expectation_map, twiddles
+
+logger = getLogger(__name__)
+
+EXPECTATION = tuple(EXPECTATION_AXES)
+TIKHONOV_REGULARIZATION_FACTOR = 1e-12  # connectivity.py:79
+
+# measure -> (needs, epilogue code or None, complex output?)
+_PAIRWISE = {
+    "coherency": ("csm", _lib.M_COHERENCY, True),
+    "coherence_magnitude": ("csm", _lib.M_COHERENCE_MAG, False),
+    "coherence_phase": ("csm", _lib.M_COHERENCE_PHASE, False),
+    "imaginary_coherence": ("csm", _lib.M_IMAG_COHERENCE, False),
+    "phase_locking_value": ("plv", _lib.M_PLV, False),
+    "pairwise_phase_consistency": ("plv", _lib.M_PPC, False),
+    "phase_lag_index": ("pli", _lib.M_PLI, False),
+    "weighted_phase_lag_index": ("pli", _lib.M_WPLI, False),
+    "debiased_squared_phase_lag_index": ("pli", _lib.M_DPLI2, False),
+    "debiased_squared_weighted_phase_lag_index": ("pli", _lib.M_DWPLI2, False),
+}
+_GRANGER_OK = ("trials_tapers", "time_trials", "time_tapers", "time_trials_tapers")
+MEASURES = ("power", "expectation_cross_spectral_matrix", "_phase_locking_value",
+            "pairwise_spectral_granger_prediction") + tuple(_PAIRWISE)
+
+
+def _expectation_error(expectation_type):
+    words = set(str(expectation_type).split("_"))
+    msg = (f"Invalid expectation_type '{expectation_type}' is not supported.\n"
+           "This parameter controls which dimensions to average over when computing the "
+           "cross-spectral matrix.\n")
+    if words.issubset({"time", "trials", "tapers"}):
+        for key in EXPECTATION:
+            if set(key.split("_")) == words:
+                msg += f"\nDid you mean '{key}'? (The words must be in a specific order)\n"
+                break
+    msg += "\nValid options are:\n" + "".join(f"  - '{k}'\n" for k in sorted(EXPECTATION))
+    msg += "\nMost common: 'trials_tapers' (average over both trials and tapers)"
+    return msg
+
+
+class Connectivity:
+    """Connectivity measures from multitaper Fourier coefficients.
+
+    Parameters follow the reference (connectivity.py:277-285).  ``fourier_coefficients`` is
+    a 5-D complex array (n_time_windows, n_trials, n_tapers, n_fft_samples, n_signals),
+    NumPy or torch.  Extra keyword-only options: ``output`` ("numpy" | "torch"),
+    ``max_chunk_bytes`` (planar-coefficient budget per streamed window chunk) and
+    ``reduce_group`` (a torch.distributed group whose ranks hold disjoint observation
+    shards -- e.g. trials -- of the same windows; partial sums are all-reduced).
+    """
+
+    def __init__(self, fourier_coefficients, expectation_type="trials_tapers", frequencies=None,
+                 time=None, blocks=None, dtype=np.complex128, *, output="numpy",
+                 max_chunk_bytes=4 << 30, reduce_group=None, _multitaper=None):
+        self._mt = _multitaper
+        if _multitaper is None:
+            if fourier_coefficients.ndim != 5:
+                raise ValueError(
+                    f"fourier_coefficients must be 5-dimensional, got {fourier_coefficients.ndim}D array.\n"
+                    "Expected shape: (n_time_windows, n_trials, n_tapers, n_fft_samples, n_signals)\n"
+                    f"Got shape: {tuple(fourier_coefficients.shape)}\n\n"
+                    "If you have time series data, use the Multitaper class to transform it:\n"
+                    "  m = Multitaper(time_series, sampling_frequency=your_fs, ...)\n"
+                    "  fourier_coefficients = m.fft()")
+        if expectation_type not in EXPECTATION_AXES:
+            raise ValueError(_expectation_error(expectation_type))
+        if output not in ("numpy", "torch"):
+            raise ValueError("output must be 'numpy' or 'torch'")
+        if not torch.cuda.is_available():
+            raise RuntimeError("spectral_connectivity_b200 needs a CUDA device; there is no CPU fallback.")
+        self._device = torch.device("cuda", torch.cuda.current_device())
+        if _multitaper is None:
+            coef = fourier_coefficients
+            if not isinstance(coef, torch.Tensor):
+                coef = torch.from_numpy(np.ascontiguousarray(coef))
+            if not coef.is_complex():
+                coef = coef.to(torch.float32).to(torch.complex64)
+            self._coef = coef.to(self._device, non_blocking=True).to(torch.complex64).contiguous()
+            if not bool(torch.isfinite(torch.view_as_real(self._coef)).all()):
+                warnings.warn("fourier_coefficients contains NaN or Inf values. Check the input time "
+                              "series, the windowing parameters and any preprocessing.", UserWarning,
+                              stacklevel=2)
+            self._shape = tuple(self._coef.shape)
+            self._hermitian = False
+        else:
+            m = _multitaper
+            self._coef = None
+            self._shape = (m.n_time_windows, m.n_trials, m.n_tapers_effective, m.n_fft_samples, m.n_signals)
+            self._hermitian = True  # real time series: X(-f) = conj X(f)
+        self.expectation_type = expectation_type
+        self._frequencies = frequencies
+        self._blocks = blocks
+        self._dtype = dtype
+        self._output = output
+        self._max_chunk_bytes = int(max_chunk_bytes)
+        self._reduce_group = reduce_group
+        self.time = time if not isinstance(time, torch.Tensor) else time.cpu().numpy()
+        self.last_granger_iterations = None
+        self.last_granger_flags = None
+
+    @classmethod
+    def from_multitaper(cls, multitaper_instance, expectation_type="trials_tapers", blocks=None,
+                        dtype=np.complex128, **kwargs):
+        """Fused path (connectivity.py:366-400): the coefficients are produced window chunk by
+        window chunk straight into the layout the CSM kernels read; ``m.fft()`` is not
+        materialised."""
+        return cls(None, expectation_type=expectation_type, time=multitaper_instance.time,
+                   frequencies=multitaper_instance.frequencies, blocks=blocks, dtype=dtype,
+                   _multitaper=multitaper_instance, **kwargs)
+
+    # ---- bookkeeping ---------------------------------------------------------------
+    @property
+    def fourier_coefficients(self):
+        if self._coef is None:
+            self._coef = self._mt.fft()
+        return self._coef
+
+    @property
+    def frequencies(self):
+        """Non-negative frequencies with the Nyquist sign fix (connectivity.py:402-424)."""
+        if self._frequencies is None:
+            return None
+        freqs = np.asarray(self._frequencies)
+        freqs = freqs[: len(freqs) // 2 + 1]
+        if len(freqs) > 0 and freqs[-1] < 0:
+            freqs = freqs.copy()
+            freqs[-1] = abs(freqs[-1])
+        return freqs
+
+    @property
+    def all_frequencies(self):
+        return None if self._frequencies is None else np.asarray(self._frequencies)
+
+    @property
+    def n_observations(self):
+        """connectivity.py:594-610."""
+        n = int(np.prod([self._shape[a] for a in EXPECTATION_AXES[self.expectation_type]]))
+        if self._reduce_group is not None:
+            import torch.distributed as dist
+            n *= dist.get_world_size(self._reduce_group)
+        return n
+
+    def _finish(self, t):
+        if self._output == "torch":
+            return t
+        return t.cpu().numpy()
+
+    # ---- streaming engine ----------------------------------------------------------
+    def _chunks(self, n_freq):
+        """Yield (b0, b1, planar chunk [b1-b0][n_freq][2][R][S], R)."""
+        lib = _lib.load()
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        time_kept = 0 not in EXPECTATION_AXES[self.expectation_type]
+        if time_kept:
+            per_window = n_trials * n_tapers * n_freq * n_sig * 8
+            wc = max(1, min(n_win, self._max_chunk_bytes // max(per_window, 1)))
+        else:
+            wc = n_win
+        for w0 in range(0, n_win, wc):
+            w1 = min(n_win, w0 + wc)
+            mapping, kept, nb, nr = expectation_map((w1 - w0, n_trials, n_tapers), self.expectation_type)
+            xp = torch.empty((nb, n_freq, 2, nr, n_sig), dtype=torch.float32, device=self._device)
+            if self._mt is not None:
+                self._mt._transform(xp, _lib.LAYOUT_PLANAR, n_freq, w0, w1 - w0, 0, mapping, nr)
+            else:
+                rc = lib.sc_repack_coefficients(_lib.ptr(self._coef[w0:w1]), w1 - w0, n_trials, n_tapers,
+                                                nfft, n_sig, n_freq, _lib.map6(mapping), nr, _lib.ptr(xp),
+                                                _lib.stream_ptr())
+                _lib.check(rc, "sc_repack_coefficients")
+            bw = nb // (w1 - w0) if time_kept else nb
+            b0 = w0 * bw if time_kept else 0
+            yield b0, b0 + nb, xp, nr
+
+    def _kept_dims(self):
+        return tuple(self._shape[a] for a in range(3) if a not in EXPECTATION_AXES[self.expectation_type])
+
+    def _allreduce(self, t):
+        if self._reduce_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._reduce_group)
+        return t
+
+    def compute(self, measures, pairs=None, tolerance=1e-8, max_iterations=60):
+        """Compute several measures in ONE streaming pass over window chunks.
+
+        ``measures``: iterable of names from ``MEASURES``.  Returns {name: array}.  Per chunk
+        the Fourier coefficients, power and cross-spectral matrix are produced once and
+        shared by all requested measures (the reference recomputes them per measure,
+        connectivity.py:146-148 of SURVEY.md section 3.3)."""
+        lib = _lib.load()
+        measures = list(measures)
+        for name in measures:
+            if name not in MEASURES:
+                raise ValueError(f"unknown measure '{name}'")
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        fnn = nfft // 2 + 1
+        want_granger = "pairwise_spectral_granger_prediction" in measures
+        if want_granger and self.expectation_type not in _GRANGER_OK:
+            raise NotImplementedError(
+                f"pairwise_spectral_granger_prediction with expectation_type='{self.expectation_type}' couples "
+                "the Wilson convergence test across a kept axis (minimum_phase_decomposition.py:290, "
+                ":313-315); only " + ", ".join(_GRANGER_OK) + " are supported.")
+        two_sided = want_granger and not self._hermitian
+        n_freq = nfft if two_sided else fnn
+        kept = self._kept_dims()
+        n_batch = int(np.prod(kept)) if kept else 1
+        dev = self._device
+        scale = 1.0 / self.n_observations
+        needs = set()
+        for name in measures:
+            if name in _PAIRWISE:
+                needs.add(_PAIRWISE[name][0])
+        if "_phase_locking_value" in measures:
+            needs.add("plv")
+        if want_granger or "expectation_cross_spectral_matrix" in measures:
+            needs.add("csm")
+        need_power = want_granger or "power" in measures or any(
+            m in measures for m in ("coherency", "coherence_magnitude", "coherence_phase", "imaginary_coherence"))
+
+        out = {}
+        for name in measures:
+            if name == "power":
+                out[name] = torch.empty((n_batch, n_freq, n_sig), dtype=torch.float32, device=dev)
+            elif name == "pairwise_spectral_granger_prediction":
+                out[name] = torch.full((n_batch, fnn, n_sig, n_sig), float("nan"), dtype=torch.float32, device=dev)
+            elif name in ("expectation_cross_spectral_matrix", "_phase_locking_value", "coherency"):
+                out[name] = torch.empty((n_batch, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
+            else:
+                out[name] = torch.empty((n_batch, n_freq, n_sig, n_sig), dtype=torch.float32, device=dev)
+
+        pair_t = None
+        n_pairs = n_sig * (n_sig - 1) // 2
+        if want_granger:
+            if pairs is not None:
+                pair_np = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+                if pair_np.size and (pair_np.min() < 0 or pair_np.max() >= n_sig):
+                    raise ValueError("pairs contain signal indices outside [0, n_signals)")
+                if (pair_np[:, 0] == pair_np[:, 1]).any():
+                    raise ValueError("pairs must reference two different signals")
+                pair_t = torch.from_numpy(pair_np).to(dev)
+                n_pairs = pair_np.shape[0]
+            ws_bytes = lib.sc_wilson_workspace_bytes(nfft)
+            gr_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            tw128 = twiddles(nfft, torch.complex128, dev)
+            it_all = torch.zeros((n_pairs, n_batch), dtype=torch.int32, device=dev)
+            fl_all = torch.zeros((n_pairs, n_batch), dtype=torch.int32, device=dev)
+
+        st = _lib.stream_ptr()
+        for b0, b1, xp, nr in self._chunks(n_freq):
+            nb = b1 - b0
+            power = csm = None
+            if need_power:
+                power = torch.empty((nb, n_freq, n_sig), dtype=torch.float32, device=dev)
+                _lib.check(lib.sc_power(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.ptr(power), st), "sc_power")
+                self._allreduce(power)
+                if "power" in out:
+                    out["power"][b0:b1] = power
+            if "csm" in needs:
+                csm = torch.empty((nb, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
+                _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(csm), st),
+                           "sc_csm")
+                self._allreduce(csm)
+                if "expectation_cross_spectral_matrix" in out:
+                    out["expectation_cross_spectral_matrix"][b0:b1] = csm
+            plv = pli = None
+            if "plv" in needs:
+                plv = torch.empty((nb, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
+                _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_PLV, _lib.ptr(plv), st),
+                           "sc_csm[plv]")
+                self._allreduce(plv)
+                if "_phase_locking_value" in out:
+                    out["_phase_locking_value"][b0:b1] = plv
+            if "pli" in needs:
+                pli = torch.empty((4, nb, n_freq, n_sig, n_sig), dtype=torch.float32, device=dev)
+                _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_PLI, _lib.ptr(pli), st),
+                           "sc_csm[pli]")
+                self._allreduce(pli)
+            del xp
+            for name in measures:
+                if name not in _PAIRWISE:
+                    continue
+                src_kind, code, _ = _PAIRWISE[name]
+                src = {"csm": csm, "plv": plv, "pli": pli}[src_kind]
+                dst = out[name][b0:b1]
+                _lib.check(lib.sc_pairwise_epilogue(code, _lib.ptr(src), _lib.ptr(power) if src_kind == "csm" else None,
+                                                    nb, n_freq, n_sig, float(self.n_observations), _lib.ptr(dst), st),
+                           f"sc_pairwise_epilogue[{name}]")
+            if want_granger:
+                it_c = torch.zeros((n_pairs, nb), dtype=torch.int32, device=dev)
+                fl_c = torch.zeros((n_pairs, nb), dtype=torch.int32, device=dev)
+                dst = out["pairwise_spectral_granger_prediction"][b0:b1]
+                rc = lib.sc_granger_pairwise(_lib.ptr(csm), _lib.ptr(power), nb, n_freq, nfft, 1 if self._hermitian else 0,
+                                             n_sig, _lib.ptr(pair_t), n_pairs, float(tolerance), int(max_iterations),
+                                             _lib.ptr(tw128), _lib.ptr(dst), _lib.ptr(it_c), _lib.ptr(fl_c),
+                                             _lib.ptr(gr_ws), ws_bytes, st)
+                _lib.check(rc, "sc_granger_pairwise")
+                it_all[:, b0:b1] = it_c
+                fl_all[:, b0:b1] = fl_c
+
+        if want_granger:
+            self.last_granger_iterations = it_all
+            self.last_granger_flags = fl_all
+            n_bad = int((fl_all & _lib.FLAG_NOT_CONVERGED).ne(0).sum())
+            n_spd = int((fl_all & _lib.FLAG_NOT_SPD).ne(0).sum())
+            if n_bad:  # minimum_phase_decomposition.py:318-322
+                logger.warning(f"Maximum iterations reached. {fl_all.numel() - n_bad} of {fl_all.numel()} converged")
+            if n_spd:  # minimum_phase_decomposition.py:78-82 (the reference falls back to a random start)
+                logger.warning(f"Computing the initial conditions using the Cholesky failed for {n_spd} "
+                               "(pair, window) problems; their Granger values are NaN.")
+
+        result = {}
+        for name, t in out.items():
+            if t.shape[1] != fnn:
+                t = t[:, :fnn]
+            tail = tuple(t.shape[1:])
+            result[name] = self._finish(t.reshape(kept + tail))
+        return result
+
+    def _one(self, name, **kw):
+        return self.compute([name], **kw)[name]
+
+    # ---- reference-named measures -------------------------------------------------------
+    def _two_sided(self, name):
+        """Expectation over all Nfft bins (the reference's private two-sided quantities)."""
+        lib = _lib.load()
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        kept = self._kept_dims()
+        n_batch = int(np.prod(kept)) if kept else 1
+        scale = 1.0 / self.n_observations
+        shape = (n_batch, nfft, n_sig) if name == "power" else (n_batch, nfft, n_sig, n_sig)
+        dtype = torch.float32 if name == "power" else torch.complex64
+        out = torch.empty(shape, dtype=dtype, device=self._device)
+        st = _lib.stream_ptr()
+        for b0, b1, xp, nr in self._chunks(nfft):
+            dst = out[b0:b1]
+            if name == "power":
+                _lib.check(lib.sc_power(_lib.ptr(xp), b1 - b0, nfft, nr, n_sig, scale, _lib.ptr(dst), st), "sc_power")
+            else:
+                _lib.check(lib.sc_csm(_lib.ptr(xp), b1 - b0, nfft, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(dst), st),
+                           "sc_csm")
+            self._allreduce(dst)
+        return self._finish(out.reshape(kept + tuple(out.shape[1:])))
+
+    @property
+    def _power(self):
+        """Two-sided E[|X|^2] (connectivity.py:441-445)."""
+        return self._two_sided("power")
+
+    def _expectation_cross_spectral_matrix(self, fcn=None, dtype=None):
+        """Two-sided expected cross-spectral matrix (connectivity.py:463-526).  Arbitrary Python
+        ``fcn`` callbacks cannot run inside the fused kernels; the measures that need one
+        (PLV, PLI family) have dedicated device modes."""
+        if fcn is not None:
+            raise NotImplementedError("per-observation callbacks are fused on the device; use the measure methods")
+        return self._two_sided("csm")
+
+    @property
+    def _cross_spectral_matrix(self):
+        """Un-averaged X_i conj(X_j), shape (W,T,K,Nfft,S,S) (connectivity.py:447-461).  Provided for
+        API parity; the measures never materialise it."""
+        lib = _lib.load()
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        coef = self.fourier_coefficients
+        nb = n_win * n_trials * n_tapers
+        xp = torch.empty((nb, nfft, 2, 1, n_sig), dtype=torch.float32, device=self._device)
+        mapping = (n_trials * n_tapers, n_tapers, 1, 0, 0, 0)
+        _lib.check(lib.sc_repack_coefficients(_lib.ptr(coef), n_win, n_trials, n_tapers, nfft, n_sig, nfft,
+                                              _lib.map6(mapping), 1, _lib.ptr(xp), _lib.stream_ptr()), "sc_repack")
+        out = torch.empty((nb, nfft, n_sig, n_sig), dtype=torch.complex64, device=self._device)
+        _lib.check(lib.sc_csm(_lib.ptr(xp), nb, nfft, 1, n_sig, 1.0, _lib.CSM_CROSS, _lib.ptr(out),
+                              _lib.stream_ptr()), "sc_csm")
+        return self._finish(out.reshape(n_win, n_trials, n_tapers, nfft, n_sig, n_sig))
+
+    def power(self):
+        """Power spectral density, (..., n_frequencies, n_signals) (connectivity.py:612-630)."""
+        return self._one("power")
+
+    def coherency(self):
+        """Complex coherency, NaN diagonal (connectivity.py:632-657)."""
+        return self._one("coherency")
+
+    def coherence_phase(self):
+        """connectivity.py:659-673."""
+        return self._one("coherence_phase")
+
+    def coherence_magnitude(self):
+        """Squared coherence magnitude clipped to [0, 1] (connectivity.py:675-702)."""
+        return self._one("coherence_magnitude")
+
+    def imaginary_coherence(self):
+        """connectivity.py:704-743."""
+        return self._one("imaginary_coherence")
+
+    def _phase_locking_value(self):
+        """Complex E[x/|x|] (connectivity.py:897-903)."""
+        return self._one("_phase_locking_value")
+
+    def phase_locking_value(self):
+        """connectivity.py:905-931."""
+        return self._one("phase_locking_value")
+
+    def phase_lag_index(self):
+        """connectivity.py:933-982."""
+        return self._one("phase_lag_index")
+
+    def weighted_phase_lag_index(self):
+        """connectivity.py:984-1028."""
+        return self._one("weighted_phase_lag_index")
+
+    def debiased_squared_phase_lag_index(self):
+        """connectivity.py:1030-1058."""
+        return self._one("debiased_squared_phase_lag_index")
+
+    def debiased_squared_weighted_phase_lag_index(self):
+        """connectivity.py:1060-1127."""
+        return self._one("debiased_squared_weighted_phase_lag_index")
+
+    def pairwise_phase_consistency(self):
+        """connectivity.py:1129-1159."""
+        return self._one("pairwise_phase_consistency")
+
+    def pairwise_spectral_granger_prediction(self, tolerance=1e-8, max_iterations=60):
+        """Spectral Granger prediction for every signal pair; [..., i, j] is the influence
+        j -> i (connectivity.py:1161-1191)."""
+        return self._one("pairwise_spectral_granger_prediction", tolerance=tolerance,
+                         max_iterations=max_iterations)
+
+    def subset_pairwise_spectral_granger_prediction(self, pairs, tolerance=1e-8, max_iterations=60):
+        """connectivity.py:1193-1213."""
+        return self._one("pairwise_spectral_granger_prediction", pairs=pairs, tolerance=tolerance,
+                         max_iterations=max_iterations)
+
+    def conditional_spectral_granger_prediction(self):
+        raise NotImplementedError  # connectivity.py:1215-1219
+
+    def blockwise_spectral_granger_prediction(self):
+        raise NotImplementedError  # connectivity.py:1221-1224
+
+    # ---- rows SURVEY.md section 8(f) marks "next": not part of this round's hot path ----
+    def _next_round(self, name):
+        raise NotImplementedError(
+            f"{name} is outside the round-1 hot-path scope (SURVEY.md section 8f); see DESIGN.md")
+
+    def canonical_coherence(self, group_labels):
+        self._next_round("canonical_coherence")
+
+    def global_coherence(self, max_rank=1):
+        self._next_round("global_coherence")
+
+    def directed_transfer_function(self):
+        self._next_round("directed_transfer_function")
+
+    def directed_coherence(self):
+        self._next_round("directed_coherence")
+
+    def partial_directed_coherence(self, keep_cupy=False):
+        self._next_round("partial_directed_coherence")
+
+    def generalized_partial_directed_coherence(self):
+        self._next_round("generalized_partial_directed_coherence")
+
+    def direct_directed_transfer_function(self):
+        self._next_round("direct_directed_transfer_function")
+
+    def group_delay(self, *args, **kwargs):
+        self._next_round("group_delay")
+
+    def delay(self, *args, **kwargs):
+        self._next_round("delay")
+
+    def phase_slope_index(self, *args, **kwargs):
+        self._next_round("phase_slope_index")
+
+
+def all_pairs(n_signals):
+    return np.array(list(combinations(range(n_signals), 2)), dtype=np.int32)

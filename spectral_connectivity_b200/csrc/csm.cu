@@ -1,0 +1,285 @@
+// Cross-spectral matrix + expectation, and the pairwise-measure epilogues (SIMT fp32 path).
+//
+// Replaces connectivity.py:447-526 (_cross_spectral_matrix + _expectation_cross_spectral_matrix):
+// the reference materialises the un-averaged (W,T,K,F,S,S) tensor with a k=1 batched matmul
+// (:1799-1822) and then reduces it with xp.mean (:67-75).  Here each CTA owns one 64x64 tile of
+// one (batch, frequency) matrix and contracts over the R observations directly from the planar
+// coefficient layout [B][F][2][R][S]; only upper-triangular tiles are computed and mirrored.
+// The per-observation non-linearities of PLV (:899-903) and the PLI family (:970-980,
+// :1010-1028, :1090-1127) are applied in registers before accumulation.
+//
+// The tensor-core (tcgen05) variant of SC_CSM_CROSS lives in csm_tc.cu; this file is the
+// path for small S and for the non-linear modes, which are not GEMMs.
+#include "sc_common.cuh"
+
+namespace {
+
+constexpr int TILE = 64;
+constexpr int RC = 16;
+constexpr int kThreads = 256;
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) csm_kernel(const float* __restrict__ xp, long long BF, long long R,
+                                                       long long S, float scale, float* __restrict__ out,
+                                                       int ntile) {
+    __shared__ __align__(16) float As[2][RC][TILE];
+    __shared__ __align__(16) float Bs[2][RC][TILE];
+    const long long npair = (long long)ntile * (ntile + 1) / 2;
+    const long long bf = blockIdx.x / npair;
+    long long pidx = blockIdx.x % npair;
+    // decode upper-triangular tile pair (ti <= tj)
+    int ti = 0;
+    while (pidx >= ntile - ti) {
+        pidx -= ntile - ti;
+        ++ti;
+    }
+    const int tj = ti + (int)pidx;
+    const long long i0 = (long long)ti * TILE, j0 = (long long)tj * TILE;
+    const long long plane = R * S;
+    const float* base = xp + bf * 2 * plane;
+
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    constexpr int NACC = MODE == SC_CSM_PLI ? 4 : 2;
+    float acc[NACC][4][4];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[a][u][v] = 0.f;
+
+    const int lc = threadIdx.x % TILE;  // column within tile for loads
+    const int lr = threadIdx.x / TILE;  // 0..3
+    for (long long r0 = 0; r0 < R; r0 += RC) {
+#pragma unroll
+        for (int q = 0; q < RC / 4; ++q) {
+            const int rr = lr + 4 * q;
+            const long long r = r0 + rr;
+            const bool rok = r < R;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float* src = base + c * plane + r * S;
+                As[c][rr][lc] = (rok && i0 + lc < S) ? __ldg(src + i0 + lc) : 0.f;
+                Bs[c][rr][lc] = (rok && j0 + lc < S) ? __ldg(src + j0 + lc) : 0.f;
+            }
+        }
+        __syncthreads();
+        const int rcv = (int)((R - r0) < RC ? (R - r0) : RC);
+        for (int rr = 0; rr < rcv; ++rr) {
+            const float4 are = *reinterpret_cast<const float4*>(&As[0][rr][ty * 4]);
+            const float4 aim = *reinterpret_cast<const float4*>(&As[1][rr][ty * 4]);
+            const float4 bre = *reinterpret_cast<const float4*>(&Bs[0][rr][tx * 4]);
+            const float4 bim = *reinterpret_cast<const float4*>(&Bs[1][rr][tx * 4]);
+            const float ar[4] = {are.x, are.y, are.z, are.w}, ai[4] = {aim.x, aim.y, aim.z, aim.w};
+            const float br[4] = {bre.x, bre.y, bre.z, bre.w}, bi[4] = {bim.x, bim.y, bim.z, bim.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if (MODE == SC_CSM_CROSS) {
+                        acc[0][u][v] = fmaf(ar[u], br[v], fmaf(ai[u], bi[v], acc[0][u][v]));
+                        acc[1][u][v] = fmaf(ai[u], br[v], fmaf(-ar[u], bi[v], acc[1][u][v]));
+                    } else if (MODE == SC_CSM_PLV) {
+                        const float pr = fmaf(ar[u], br[v], ai[u] * bi[v]);
+                        const float pi = fmaf(ai[u], br[v], -ar[u] * bi[v]);
+                        const float inv = 1.0f / sqrtf(fmaf(pr, pr, pi * pi));
+                        acc[0][u][v] += pr * inv;  // 0/0 -> NaN like numpy x/abs(x)
+                        acc[1][u][v] += pi * inv;
+                    } else {
+                        float im = fmaf(ai[u], br[v], -ar[u] * bi[v]);
+                        if (i0 + ty * 4 + u == j0 + tx * 4 + v) im = 0.f;
+                        acc[0][u][v] += (im > 0.f) ? 1.f : ((im < 0.f) ? -1.f : im);  // sign, NaN propagates
+                        acc[1][u][v] += fabsf(im);
+                        acc[2][u][v] = fmaf(im, im, acc[2][u][v]);
+                        acc[3][u][v] += im;
+                    }
+                }
+        }
+        __syncthreads();
+    }
+
+    const long long mat = bf * S * S;
+    const long long pstride = BF * S * S;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const long long i = i0 + ty * 4 + u;
+        if (i >= S) continue;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const long long j = j0 + tx * 4 + v;
+            if (j >= S) continue;
+            if (MODE == SC_CSM_PLI) {
+                const float sg[4] = {-1.f, 1.f, 1.f, -1.f};  // mirror signs: sign(Im), |Im|, Im^2, Im
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const float val = acc[a][u][v] * scale;
+                    out[a * pstride + mat + i * S + j] = val;
+                    if (ti != tj) out[a * pstride + mat + j * S + i] = sg[a] * val;
+                }
+            } else {
+                float2* o = reinterpret_cast<float2*>(out);
+                const float2 val = make_float2(acc[0][u][v] * scale, acc[1][u][v] * scale);
+                o[mat + i * S + j] = val;
+                if (ti != tj) o[mat + j * S + i] = make_float2(val.x, -val.y);
+            }
+        }
+    }
+}
+
+__global__ void power_kernel(const float* __restrict__ xp, long long BF, long long R, long long S, float scale,
+                             float* __restrict__ out) {
+    const long long total = BF * S;
+    const long long plane = R * S;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long bf = idx / S, s = idx % S;
+        const float* re = xp + bf * 2 * plane + s;
+        const float* im = re + plane;
+        float a0 = 0.f, a1 = 0.f;
+        long long r = 0;
+        for (; r + 1 < R; r += 2) {
+            const float x0 = __ldg(re + r * S), y0 = __ldg(im + r * S);
+            const float x1 = __ldg(re + (r + 1) * S), y1 = __ldg(im + (r + 1) * S);
+            a0 = fmaf(x0, x0, fmaf(y0, y0, a0));
+            a1 = fmaf(x1, x1, fmaf(y1, y1, a1));
+        }
+        if (r < R) {
+            const float x0 = __ldg(re + r * S), y0 = __ldg(im + r * S);
+            a0 = fmaf(x0, x0, fmaf(y0, y0, a0));
+        }
+        out[idx] = (a0 + a1) * scale;
+    }
+}
+
+constexpr double kEps64 = 2.220446049250313e-16;
+
+__global__ void epilogue_kernel(int measure, const float* __restrict__ in0, const float* __restrict__ in1,
+                                long long BF, long long S, double nobs, float* __restrict__ out) {
+    const long long total = BF * S * S;
+    const float qnan = __int_as_float(0x7fc00000);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long j = idx % S;
+        const long long i = (idx / S) % S;
+        const long long bf = idx / (S * S);
+        switch (measure) {
+            case SC_M_COHERENCY:
+            case SC_M_COHERENCE_MAG:
+            case SC_M_COHERENCE_PHASE:
+            case SC_M_IMAG_COHERENCE: {
+                const float2 c = reinterpret_cast<const float2*>(in0)[idx];
+                const double pi_ = in1[bf * S + i], pj = in1[bf * S + j];
+                double norm = sqrt(pi_ * pj);
+                norm = norm > kEps64 ? norm : kEps64;  // connectivity.py:649-652
+                const double re = c.x / norm, im = c.y / norm;
+                if (measure == SC_M_COHERENCY) {
+                    reinterpret_cast<float2*>(out)[idx] = i == j ? make_float2(qnan, qnan) : make_float2((float)re, (float)im);
+                } else if (measure == SC_M_COHERENCE_MAG) {
+                    double m = re * re + im * im;
+                    m = m < 0.0 ? 0.0 : (m > 1.0 ? 1.0 : m);
+                    out[idx] = i == j ? qnan : (float)m;
+                } else if (measure == SC_M_COHERENCE_PHASE) {
+                    out[idx] = i == j ? qnan : (float)atan2(im, re);
+                } else {
+                    double m = fabs(im);
+                    m = m > 1.0 ? 1.0 : m;
+                    out[idx] = (float)m;
+                }
+                break;
+            }
+            case SC_M_PLV: {
+                const float2 c = reinterpret_cast<const float2*>(in0)[idx];
+                out[idx] = (float)sqrt((double)c.x * c.x + (double)c.y * c.y);
+                break;
+            }
+            case SC_M_PPC: {
+                const float2 c = reinterpret_cast<const float2*>(in0)[idx];
+                const double sx = c.x * nobs, sy = c.y * nobs;
+                out[idx] = (float)((sx * sx + sy * sy - nobs) / (nobs * nobs - nobs));
+                break;
+            }
+            case SC_M_PLI: out[idx] = in0[idx]; break;
+            case SC_M_DPLI2: {
+                const double p = in0[idx];
+                out[idx] = (float)((nobs * p * p - 1.0) / (nobs - 1.0));
+                break;
+            }
+            case SC_M_WPLI: {
+                double w = in0[total + idx];
+                if (w < kEps64) w = 1.0;  // connectivity.py:1027
+                out[idx] = (float)((double)in0[3 * total + idx] / w);
+                break;
+            }
+            case SC_M_DWPLI2: {
+                const double s_abs = (double)in0[total + idx] * nobs;
+                const double s_sq = (double)in0[2 * total + idx] * nobs;
+                const double s_im = (double)in0[3 * total + idx] * nobs;
+                const double w = s_abs * s_abs - s_sq;
+                out[idx] = w == 0.0 ? qnan : (float)((s_im * s_im - s_sq) / w);  // connectivity.py:1125-1127
+                break;
+            }
+            default: break;
+        }
+    }
+}
+
+unsigned grid_for(long long total, int threads) {
+    long long blocks = (total + threads - 1) / threads;
+    const long long cap = (long long)sc_num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace
+
+extern "C" int sc_power(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, float scale, float* out,
+                        void* stream) {
+    SC_CHECK_ARG(xp && out, "sc_power: null pointer");
+    SC_CHECK_ARG(B > 0 && F > 0 && R > 0 && S > 0, "sc_power: non-positive size");
+    power_kernel<<<grid_for(B * F * S, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(xp, B * F, R, S, scale,
+                                                                                              out);
+    SC_LAUNCH_OK();
+    return SC_OK;
+}
+
+int sc_csm_tc_supported(int64_t R, int64_t S);
+int sc_csm_tc_launch(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, float scale, void* out,
+                     cudaStream_t st);
+
+extern "C" int sc_csm_simt(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, float scale, int mode,
+                           void* out, void* stream) {
+    SC_CHECK_ARG(xp && out, "sc_csm: null pointer");
+    SC_CHECK_ARG(B > 0 && F > 0 && R > 0 && S > 0, "sc_csm: non-positive size");
+    SC_CHECK_ARG(mode >= 0 && mode <= 2, "sc_csm: unknown mode %d", mode);
+    const int ntile = (int)((S + TILE - 1) / TILE);
+    const long long npair = (long long)ntile * (ntile + 1) / 2;
+    const long long grid = npair * B * F;
+    SC_CHECK_ARG(grid < (1LL << 31), "sc_csm: grid too large (%lld CTAs); split the batch", grid);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    float* o = reinterpret_cast<float*>(out);
+    if (mode == SC_CSM_CROSS) csm_kernel<SC_CSM_CROSS><<<(unsigned)grid, kThreads, 0, st>>>(xp, B * F, R, S, scale, o, ntile);
+    else if (mode == SC_CSM_PLV) csm_kernel<SC_CSM_PLV><<<(unsigned)grid, kThreads, 0, st>>>(xp, B * F, R, S, scale, o, ntile);
+    else csm_kernel<SC_CSM_PLI><<<(unsigned)grid, kThreads, 0, st>>>(xp, B * F, R, S, scale, o, ntile);
+    SC_LAUNCH_OK();
+    return SC_OK;
+}
+
+extern "C" int sc_csm(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, float scale, int mode, void* out,
+                      void* stream) {
+    if (mode == SC_CSM_CROSS && xp && out && sc_csm_tc_supported(R, S))
+        return sc_csm_tc_launch(xp, B, F, R, S, scale, out, reinterpret_cast<cudaStream_t>(stream));
+    return sc_csm_simt(xp, B, F, R, S, scale, mode, out, stream);
+}
+
+extern "C" int sc_pairwise_epilogue(int measure, const void* in0, const float* in1, int64_t B, int64_t F, int64_t S,
+                                    double n_observations, void* out, void* stream) {
+    SC_CHECK_ARG(in0 && out, "sc_pairwise_epilogue: null pointer");
+    SC_CHECK_ARG(measure >= SC_M_COHERENCY && measure <= SC_M_DWPLI2, "sc_pairwise_epilogue: unknown measure %d", measure);
+    SC_CHECK_ARG(measure > SC_M_IMAG_COHERENCE || in1, "sc_pairwise_epilogue: measure %d needs the power array", measure);
+    SC_CHECK_ARG(B > 0 && F > 0 && S > 0, "sc_pairwise_epilogue: non-positive size");
+    epilogue_kernel<<<grid_for(B * F * S * S, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        measure, reinterpret_cast<const float*>(in0), in1, B * F, S, n_observations, reinterpret_cast<float*>(out));
+    SC_LAUNCH_OK();
+    return SC_OK;
+}

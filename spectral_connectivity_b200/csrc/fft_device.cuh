@@ -1,0 +1,299 @@
+// CTA-cooperative mixed-radix Stockham FFT for arbitrary lengths.
+//
+// Used by both hot kernels: the fused multitaper FFT (fp32, replaces the reference's
+// scipy.fft.fft call at transforms.py:1405) and the Wilson factorisation (fp64,
+// replaces the fft/ifft pair at minimum_phase_decomposition.py:129-142).
+//
+// The butterflies are plain host/device templates so that tests/cpu/fft_host_test.cpp
+// can compile this header with g++ and check the index arithmetic against numpy
+// without a GPU.  Only sc_cta_fft() (the part that touches threadIdx/__syncthreads)
+// is CUDA-only.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SC_HD __host__ __device__ __forceinline__
+#else
+#define SC_HD inline
+#endif
+
+#define SC_FFT_MAX_STAGES 32
+
+struct ScFftPlan {
+    int n;
+    int nstages;
+    int radix[SC_FFT_MAX_STAGES];
+};
+
+// Factorise n into the radices the device code has register butterflies for
+// (10, 8, 5, 4, 3, 2, 7, 11, 13); any other prime factor p becomes one O(p^2)
+// "generic" stage.  Returns 0 on success.
+static inline int sc_fft_make_plan(int n, ScFftPlan* p) {
+    p->n = n;
+    p->nstages = 0;
+    if (n < 1) return -1;
+    int m = n;
+    const int pref[] = {10, 8, 5, 4, 3, 2, 7, 11, 13};
+    for (int i = 0; i < 9; ++i) {
+        const int r = pref[i];
+        while (m % r == 0) {
+            if (p->nstages >= SC_FFT_MAX_STAGES) return -1;
+            p->radix[p->nstages++] = r;
+            m /= r;
+        }
+    }
+    for (int q = 17; m > 1; q += 2) {
+        if ((long long)q * q > m) q = m;  // remaining m is prime
+        while (m % q == 0) {
+            if (p->nstages >= SC_FFT_MAX_STAGES) return -1;
+            p->radix[p->nstages++] = q;
+            m /= q;
+        }
+    }
+    return 0;
+}
+
+template <typename R>
+struct alignas(2 * sizeof(R)) cx {
+    R x, y;
+};
+
+template <typename R> SC_HD cx<R> cmake(R a, R b) { cx<R> r; r.x = a; r.y = b; return r; }
+template <typename R> SC_HD cx<R> cadd(cx<R> a, cx<R> b) { return cmake<R>(a.x + b.x, a.y + b.y); }
+template <typename R> SC_HD cx<R> csub(cx<R> a, cx<R> b) { return cmake<R>(a.x - b.x, a.y - b.y); }
+template <typename R> SC_HD cx<R> cmul(cx<R> a, cx<R> b) {
+    return cmake<R>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+template <typename R> SC_HD cx<R> cconj(cx<R> a) { return cmake<R>(a.x, -a.y); }
+template <typename R> SC_HD cx<R> cscale(cx<R> a, R s) { return cmake<R>(a.x * s, a.y * s); }
+// multiply by -i (forward) or +i (inverse)
+template <typename R> SC_HD cx<R> cmul_mi(cx<R> a, bool inv) {
+    return inv ? cmake<R>(-a.y, a.x) : cmake<R>(a.y, -a.x);
+}
+
+// ---------------------------------------------------------------------------
+// register butterflies: v <- DFT_r(v) (forward: exp(-2 pi i/r), inverse: conj)
+// ---------------------------------------------------------------------------
+template <typename R> SC_HD void sc_dft2(cx<R>& a, cx<R>& b) {
+    cx<R> t = csub(a, b);
+    a = cadd(a, b);
+    b = t;
+}
+
+template <typename R> SC_HD void sc_dft3(cx<R>* v, bool inv) {
+    const R s = (R)0.86602540378443864676372317075294;  // sin(pi/3)
+    cx<R> t1 = cadd(v[1], v[2]);
+    cx<R> t2 = cmake<R>(v[0].x - (R)0.5 * t1.x, v[0].y - (R)0.5 * t1.y);
+    cx<R> d = csub(v[1], v[2]);
+    cx<R> t3 = cmul_mi(cscale(d, s), inv);  // -i*s*(v1-v2) forward
+    v[0] = cadd(v[0], t1);
+    v[1] = cadd(t2, t3);
+    v[2] = csub(t2, t3);
+}
+
+template <typename R> SC_HD void sc_dft4(cx<R>* v, bool inv) {
+    cx<R> a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
+    cx<R> c = cadd(v[1], v[3]), d = cmul_mi(csub(v[1], v[3]), inv);
+    v[0] = cadd(a, c);
+    v[1] = cadd(b, d);
+    v[2] = csub(a, c);
+    v[3] = csub(b, d);
+}
+
+template <typename R> SC_HD void sc_dft5(cx<R>* v, bool inv) {
+    const R c1 = (R)0.30901699437494742410229341718282;   // cos(2pi/5)
+    const R c2 = (R)-0.80901699437494742410229341718282;  // cos(4pi/5)
+    const R s1 = (R)0.95105651629515357211643933337938;   // sin(2pi/5)
+    const R s2 = (R)0.58778525229247312916870595463907;   // sin(4pi/5)
+    cx<R> a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
+    cx<R> a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
+    cx<R> m1 = cmake<R>(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
+    cx<R> m2 = cmake<R>(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
+    cx<R> n1 = cmul_mi(cmake<R>(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y), inv);
+    cx<R> n2 = cmul_mi(cmake<R>(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y), inv);
+    v[0] = cadd(v[0], cadd(a1, a2));
+    v[1] = cadd(m1, n1);
+    v[4] = csub(m1, n1);
+    v[2] = cadd(m2, n2);
+    v[3] = csub(m2, n2);
+}
+
+template <typename R> SC_HD void sc_dft8(cx<R>* v, bool inv) {
+    const R h = (R)0.70710678118654752440084436210485;
+    // decimation in frequency: 8 = 2 x 4
+    cx<R> e[4], o[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        e[a] = cadd(v[a], v[a + 4]);
+        o[a] = csub(v[a], v[a + 4]);
+    }
+    // o[a] *= W8^a
+    {
+        cx<R> t = o[1];  // W8^1 = h(1 - i) forward, h(1 + i) inverse
+        o[1] = inv ? cmake<R>(h * (t.x - t.y), h * (t.x + t.y)) : cmake<R>(h * (t.x + t.y), h * (t.y - t.x));
+        o[2] = cmul_mi(o[2], inv);
+        t = o[3];  // W8^3 = h(-1 - i) forward, h(-1 + i) inverse
+        o[3] = inv ? cmake<R>(h * (-t.x - t.y), h * (t.x - t.y)) : cmake<R>(h * (t.y - t.x), h * (-t.x - t.y));
+    }
+    sc_dft4(e, inv);
+    sc_dft4(o, inv);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        v[2 * q] = e[q];
+        v[2 * q + 1] = o[q];
+    }
+}
+
+template <typename R> SC_HD void sc_dft10(cx<R>* v, bool inv) {
+    // decimation in frequency: 10 = 2 x 5; W10^a = exp(-2 pi i a/10)
+    const R wc[5] = {(R)1.0, (R)0.80901699437494742410229341718282, (R)0.30901699437494742410229341718282,
+                     (R)-0.30901699437494742410229341718282, (R)-0.80901699437494742410229341718282};
+    const R ws[5] = {(R)0.0, (R)0.58778525229247312916870595463907, (R)0.95105651629515357211643933337938,
+                     (R)0.95105651629515357211643933337938, (R)0.58778525229247312916870595463907};
+    cx<R> e[5], o[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        e[a] = cadd(v[a], v[a + 5]);
+        o[a] = csub(v[a], v[a + 5]);
+        if (a > 0) o[a] = cmul(o[a], cmake<R>(wc[a], inv ? ws[a] : -ws[a]));
+    }
+    sc_dft5(e, inv);
+    sc_dft5(o, inv);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        v[2 * q] = e[q];
+        v[2 * q + 1] = o[q];
+    }
+}
+
+// O(r^2) register DFT for the odd primes 7, 11, 13; roots taken from the twiddle table.
+template <typename R, int RADIX>
+SC_HD void sc_dft_prime(cx<R>* v, bool inv, const cx<R>* tw, int n) {
+    cx<R> w[RADIX];
+    const int st = n / RADIX;
+#pragma unroll
+    for (int t = 0; t < RADIX; ++t) {
+        w[t] = tw[t * st];
+        if (inv) w[t].y = -w[t].y;
+    }
+    cx<R> out[RADIX];
+#pragma unroll
+    for (int q = 0; q < RADIX; ++q) {
+        cx<R> acc = v[0];
+#pragma unroll
+        for (int t = 1; t < RADIX; ++t) acc = cadd(acc, cmul(v[t], w[(q * t) % RADIX]));
+        out[q] = acc;
+    }
+#pragma unroll
+    for (int q = 0; q < RADIX; ++q) v[q] = out[q];
+}
+
+template <typename R, int RADIX>
+SC_HD void sc_dft(cx<R>* v, bool inv, const cx<R>* tw, int n) {
+    if (RADIX == 2) sc_dft2(v[0], v[1]);
+    else if (RADIX == 3) sc_dft3(v, inv);
+    else if (RADIX == 4) sc_dft4(v, inv);
+    else if (RADIX == 5) sc_dft5(v, inv);
+    else if (RADIX == 8) sc_dft8(v, inv);
+    else if (RADIX == 10) sc_dft10(v, inv);
+    else sc_dft_prime<R, RADIX>(v, inv, tw, n);
+}
+
+// One Stockham butterfly j (0 <= j < n/RADIX) of the stage whose already-transformed
+// sub-length is Ls: reads src[j + t*n/RADIX], writes dst[(j-k)*RADIX + k + q*Ls], k = j % Ls.
+// tw[q] = exp(-2 pi i q/n), q in [0, n).
+template <typename R, int RADIX>
+SC_HD void sc_fft_item(const cx<R>* src, cx<R>* dst, int j, int n, int Ls, const cx<R>* tw, bool inv) {
+    const int m = n / RADIX;
+    const int k = j % Ls;
+    const int tws = m / Ls;  // n / (Ls*RADIX)
+    cx<R> v[RADIX];
+#pragma unroll
+    for (int t = 0; t < RADIX; ++t) v[t] = src[j + t * m];
+    if (k != 0) {
+#pragma unroll
+        for (int t = 1; t < RADIX; ++t) {
+            cx<R> w = tw[t * k * tws];  // t*k*tws < RADIX*Ls*tws = n
+            if (inv) w.y = -w.y;
+            v[t] = cmul(v[t], w);
+        }
+    }
+    sc_dft<R, RADIX>(v, inv, tw, n);
+    const int ob = (j - k) * RADIX + k;
+#pragma unroll
+    for (int q = 0; q < RADIX; ++q) dst[ob + q * Ls] = v[q];
+}
+
+// Runtime-radix fallback (large prime factors): item = (j, q) pair, 0 <= item < n.
+template <typename R>
+SC_HD void sc_fft_item_generic(const cx<R>* src, cx<R>* dst, int item, int radix, int n, int Ls,
+                               const cx<R>* tw, bool inv) {
+    const int m = n / radix;
+    const int j = item % m;
+    const int q = item / m;
+    const int k = j % Ls;
+    const int tws = m / Ls;
+    const long long base = (long long)k * tws + (long long)q * m;  // < n
+    cx<R> acc = src[j];
+    for (int t = 1; t < radix; ++t) {
+        cx<R> w = tw[(int)((base * t) % n)];
+        if (inv) w.y = -w.y;
+        acc = cadd(acc, cmul(src[j + t * m], w));
+    }
+    dst[(j - k) * radix + k + q * Ls] = acc;
+}
+
+#if defined(__CUDACC__)
+template <typename R, int RADIX>
+__device__ __forceinline__ void sc_cta_fft_pass(const cx<R>* src, cx<R>* dst, int nbatch, int bstride, int n,
+                                                int Ls, const cx<R>* tw, bool inv) {
+    const int m = n / RADIX;
+    const int total = nbatch * m;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int bb = idx / m;
+        const int j = idx - bb * m;
+        sc_fft_item<R, RADIX>(src + (size_t)bb * bstride, dst + (size_t)bb * bstride, j, n, Ls, tw, inv);
+    }
+}
+
+// nbatch FFTs of length plan.n at a + b*bstride, ping-pong with buffer b (same layout).
+// All threads of the CTA must call it; returns the buffer that holds the result.
+// Unnormalised in both directions.
+template <typename R>
+__device__ cx<R>* sc_cta_fft(cx<R>* a, cx<R>* b, int nbatch, int bstride, const ScFftPlan& plan,
+                             const cx<R>* tw, bool inv) {
+    const int n = plan.n;
+    cx<R>* src = a;
+    cx<R>* dst = b;
+    int Ls = 1;
+    for (int s = 0; s < plan.nstages; ++s) {
+        const int r = plan.radix[s];
+        switch (r) {
+            case 2: sc_cta_fft_pass<R, 2>(src, dst, nbatch, bstride, n, Ls, tw, inv); break;
+            case 3: sc_cta_fft_pass<R, 3>(src, dst, nbatch, bstride, n, Ls, tw, inv); break;
+            case 4: sc_cta_fft_pass<R, 4>(src, dst, nbatch, bstride, n, Ls, tw, inv); break;
+            case 5: sc_cta_fft_pass<R, 5>(src, dst, nbatch, bstride, n, Ls, tw, inv); break;
+            case 7: sc_cta_fft_pass<R, 7>(src, dst, nbatch, bstride, n, Ls, tw, inv); break;
+            case 8: sc_cta_fft_pass<R, 8>(src, dst, nbatch, bstride, n, Ls, tw, inv); break;
+            case 10: sc_cta_fft_pass<R, 10>(src, dst, nbatch, bstride, n, Ls, tw, inv); break;
+            case 11: sc_cta_fft_pass<R, 11>(src, dst, nbatch, bstride, n, Ls, tw, inv); break;
+            case 13: sc_cta_fft_pass<R, 13>(src, dst, nbatch, bstride, n, Ls, tw, inv); break;
+            default: {
+                const int total = nbatch * n;
+                for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+                    const int bb = idx / n;
+                    sc_fft_item_generic<R>(src + (size_t)bb * bstride, dst + (size_t)bb * bstride, idx - bb * n, r,
+                                           n, Ls, tw, inv);
+                }
+            }
+        }
+        __syncthreads();
+        Ls *= r;
+        cx<R>* t = src;
+        src = dst;
+        dst = t;
+    }
+    return src;
+}
+#endif  // __CUDACC__

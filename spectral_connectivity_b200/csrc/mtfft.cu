@@ -1,0 +1,303 @@
+// Fused multitaper FFT: sliding-window gather + detrend + DPSS taper product + real FFT.
+// Replaces transforms.py:1147-1171 (Multitaper.fft) = _sliding_window (:1311-1374) +
+// detrend (:1798-1915) + _multitaper_fft (:1377-1405), which in the reference materialise a
+// (W,T,S,n) window copy, a (W,T,S,n,K) float64 product and a two-sided complex128 FFT.
+//
+// One CTA owns one (window, trial, tile of TS signals).  The n x TS slab is loaded once
+// (coalesced along the signal axis), detrended in shared memory, and for every taper the
+// TS real series are packed two-per-complex-FFT, transformed by the CTA-cooperative Stockham
+// FFT (fft_device.cuh), unpacked to half (or full) spectra and stored with the signal axis
+// fastest, so the CSM stage reads [F][2][R][S] tiles directly.
+#include "fft_device.cuh"
+#include "sc_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWsCtas = 296;
+
+struct MtParams {
+    const float* x;
+    long long N, T, S;
+    const float* tapers;
+    int n, K, step;
+    long long w0, W, w_out0;
+    int nfft, detrend;
+    float scale;
+    const cx<float>* tw;
+    int layout, nfo;
+    ScMap map;
+    long long R;
+    void* out;
+    cx<float>* ws;
+    ScFftPlan plan;
+};
+
+template <int TS, bool WS>
+__global__ void __launch_bounds__(kThreads) mt_fft_kernel(const MtParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NP = TS / 2;  // complex FFTs per taper
+    const int n = p.n, nfft = p.nfft;
+    const int ncopy = n < nfft ? n : nfft;
+    const long long tiles = (p.S + TS - 1) / TS;
+    const long long total = p.W * p.T * tiles;
+
+    float* tile = nullptr;
+    cx<float>*bufA, *bufB;
+    const cx<float>* tw;
+    __shared__ double red[2][kThreads];
+    __shared__ float trend_a[TS], trend_b[TS];
+    if (WS) {
+        bufA = p.ws + (size_t)blockIdx.x * 2 * NP * nfft;
+        bufB = bufA + (size_t)NP * nfft;
+        tw = p.tw;
+    } else {
+        bufA = reinterpret_cast<cx<float>*>(smem_raw);
+        bufB = bufA + (size_t)NP * nfft;
+        cx<float>* tws = bufB + (size_t)NP * nfft;
+        tile = reinterpret_cast<float*>(tws + nfft);
+        for (int q = threadIdx.x; q < nfft; q += kThreads) tws[q] = p.tw[q];
+        tw = tws;
+    }
+
+    for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+        const long long tile_i = item % tiles;
+        const long long t = (item / tiles) % p.T;
+        const long long wl = item / (tiles * p.T);
+        const long long w = p.w0 + wl;
+        const long long s0 = tile_i * TS;
+        const float* xw = p.x + ((w * p.step) * p.T + t) * p.S + s0;  // + j*T*S + s
+        const long long row = p.T * p.S;
+        const int sl = threadIdx.x % TS;
+        const int jr = threadIdx.x / TS;
+        constexpr int JSTEP = kThreads / TS;
+        const bool s_ok = (s0 + sl) < p.S;
+
+        // ---- load slab + detrend statistics --------------------------------
+        double sum = 0.0, sumu = 0.0;
+        const double ubar = (n + 1.0) / (2.0 * n);
+        for (int j = jr; j < n; j += JSTEP) {
+            const float v = s_ok ? __ldg(xw + (long long)j * row + sl) : 0.f;
+            if (!WS) tile[j * TS + sl] = v;
+            sum += v;
+            sumu += ((j + 1.0) / n - ubar) * v;
+        }
+        if (p.detrend != SC_DETREND_NONE) {
+            red[0][threadIdx.x] = sum;
+            red[1][threadIdx.x] = sumu;
+            __syncthreads();
+            if (threadIdx.x < TS) {
+                double a = 0.0, b = 0.0;
+                for (int q = 0; q < JSTEP; ++q) {
+                    a += red[0][q * TS + threadIdx.x];
+                    b += red[1][q * TS + threadIdx.x];
+                }
+                const double mean = a / n;
+                double slope = 0.0;
+                if (p.detrend == SC_DETREND_LINEAR && n > 1) slope = b / ((double(n) * n - 1.0) / (12.0 * n));
+                // x' = x - slope*u - icpt, u = (j+1)/n
+                trend_a[threadIdx.x] = (float)slope;
+                trend_b[threadIdx.x] = (float)(mean - slope * ubar);
+            }
+        } else if (threadIdx.x < TS) {
+            trend_a[threadIdx.x] = 0.f;
+            trend_b[threadIdx.x] = 0.f;
+        }
+        __syncthreads();
+        if (!WS && p.detrend != SC_DETREND_NONE) {
+            const float ta = trend_a[sl], tb = trend_b[sl];
+            const float invn = 1.0f / n;
+            for (int j = jr; j < ncopy; j += JSTEP) tile[j * TS + sl] -= ta * ((j + 1) * invn) + tb;
+            __syncthreads();
+        }
+
+        for (int k = 0; k < p.K; ++k) {
+            const float* h = p.tapers + (size_t)k * n;
+            // ---- taper product, two real series per complex sequence --------
+            for (int idx = threadIdx.x; idx < NP * nfft; idx += kThreads) {
+                const int pp = idx % NP;
+                const int j = idx / NP;
+                cx<float> z = cmake<float>(0.f, 0.f);
+                if (j < ncopy) {
+                    const float hv = __ldg(h + j);
+                    float v0, v1;
+                    if (WS) {
+                        const float u = (j + 1.0f) / n;
+                        v0 = (s0 + 2 * pp < p.S) ? __ldg(xw + (long long)j * row + 2 * pp) : 0.f;
+                        v1 = (s0 + 2 * pp + 1 < p.S) ? __ldg(xw + (long long)j * row + 2 * pp + 1) : 0.f;
+                        v0 -= trend_a[2 * pp] * u + trend_b[2 * pp];
+                        v1 -= trend_a[2 * pp + 1] * u + trend_b[2 * pp + 1];
+                    } else {
+                        const float2 v = *reinterpret_cast<const float2*>(tile + j * TS + 2 * pp);
+                        v0 = v.x;
+                        v1 = v.y;
+                    }
+                    z = cmake<float>(v0 * hv, v1 * hv);
+                }
+                bufA[(size_t)pp * nfft + j] = z;
+            }
+            __syncthreads();
+            const cx<float>* res = sc_cta_fft<float>(bufA, bufB, NP, nfft, p.plan, tw, false);
+
+            // ---- unpack the two real spectra and store -----------------------
+            const long long wo = p.w_out0 + wl;
+            if (p.layout == SC_LAYOUT_PLANAR) {
+                const long long b = wo * p.map.bw + t * p.map.bt + k * p.map.bk;
+                const long long r = wo * p.map.rw + t * p.map.rt + k * p.map.rk;
+                float* out = reinterpret_cast<float*>(p.out);
+                const long long plane = p.R * p.S;
+                for (int idx = threadIdx.x; idx < p.nfo * 2 * TS; idx += kThreads) {
+                    const int s = idx % TS;
+                    const int c = (idx / TS) & 1;
+                    const int f = idx / (2 * TS);
+                    if (s0 + s >= p.S) continue;
+                    const cx<float> z1 = res[(size_t)(s >> 1) * nfft + f];
+                    const cx<float> z2 = res[(size_t)(s >> 1) * nfft + (f == 0 ? 0 : nfft - f)];
+                    float v;
+                    if ((s & 1) == 0) v = c == 0 ? (z1.x + z2.x) : (z1.y - z2.y);
+                    else v = c == 0 ? (z1.y + z2.y) : (z2.x - z1.x);
+                    out[((b * p.nfo + f) * 2 + c) * plane + r * p.S + s0 + s] = 0.5f * p.scale * v;
+                }
+            } else {
+                float2* out = reinterpret_cast<float2*>(p.out);
+                const long long base = ((wo * p.T + t) * p.K + k) * p.nfo;
+                for (int idx = threadIdx.x; idx < p.nfo * TS; idx += kThreads) {
+                    const int s = idx % TS;
+                    const int f = idx / TS;
+                    if (s0 + s >= p.S) continue;
+                    const cx<float> z1 = res[(size_t)(s >> 1) * nfft + f];
+                    const cx<float> z2 = res[(size_t)(s >> 1) * nfft + (f == 0 ? 0 : nfft - f)];
+                    float2 v;
+                    if ((s & 1) == 0) v = make_float2(z1.x + z2.x, z1.y - z2.y);
+                    else v = make_float2(z1.y + z2.y, z2.x - z1.x);
+                    v.x *= 0.5f * p.scale;
+                    v.y *= 0.5f * p.scale;
+                    out[(base + f) * p.S + s0 + s] = v;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+size_t mt_smem_bytes(int ts, int n, int nfft) {
+    return (size_t)2 * (ts / 2) * nfft * 8 + (size_t)nfft * 8 + (size_t)n * ts * 4;
+}
+
+int mt_pick_ts(int n, int nfft) {
+    const size_t cap = (size_t)sc_max_smem_optin() - 20 * 1024;  // static smem + slack
+    const int cand[3] = {8, 4, 2};
+    for (int i = 0; i < 3; ++i)
+        if (mt_smem_bytes(cand[i], n, nfft) <= cap / 2) return cand[i];
+    for (int i = 0; i < 3; ++i)
+        if (mt_smem_bytes(cand[i], n, nfft) <= cap) return cand[i];
+    return 0;  // workspace mode
+}
+
+template <int TS, bool WS>
+int mt_launch(const MtParams& p, size_t smem, long long grid, cudaStream_t st) {
+    if (smem > 48 * 1024)
+        SC_CUDA_OK(cudaFuncSetAttribute(mt_fft_kernel<TS, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mt_fft_kernel<TS, WS><<<(unsigned)grid, kThreads, smem, st>>>(p);
+    SC_LAUNCH_OK();
+    return SC_OK;
+}
+
+__global__ void repack_kernel(const float2* __restrict__ coef, long long W, long long T, long long K, long long nfft,
+                              long long S, int nfo, ScMap map, long long R, float* __restrict__ out) {
+    const long long total = W * T * K * nfo * S;
+    const long long plane = R * S;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long s = i % S;
+        long long q = i / S;
+        const long long f = q % nfo;
+        q /= nfo;
+        const long long k = q % K;
+        q /= K;
+        const long long t = q % T;
+        const long long w = q / T;
+        const float2 v = coef[(((w * T + t) * K + k) * nfft + f) * S + s];
+        const long long b = w * map.bw + t * map.bt + k * map.bk;
+        const long long r = w * map.rw + t * map.rt + k * map.rk;
+        const long long o = ((b * nfo + f) * 2) * plane + r * S + s;
+        out[o] = v.x;
+        out[o + plane] = v.y;
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t sc_mt_fft_workspace_bytes(int n, int nfft) {
+    if (n < 1 || nfft < 1) return 0;
+    if (mt_pick_ts(n, nfft) != 0) return 0;
+    return (int64_t)kWsCtas * 2 * nfft * 8;
+}
+
+extern "C" int sc_mt_fft(const float* x, int64_t N, int64_t T, int64_t S, const float* tapers, int n, int K, int step,
+                         int64_t w0, int64_t W, int64_t w_out0, int nfft, int detrend, float scale,
+                         const void* twiddle, int layout, int n_freq_out, const int64_t* map, int64_t n_reduce,
+                         void* out, void* workspace, int64_t workspace_bytes, void* stream) {
+    SC_CHECK_ARG(x && tapers && twiddle && out, "sc_mt_fft: null pointer");
+    SC_CHECK_ARG(N > 0 && T > 0 && S > 0 && n > 0 && K > 0 && step > 0 && nfft > 0, "sc_mt_fft: non-positive size");
+    SC_CHECK_ARG(W >= 0 && w0 >= 0 && (w0 + W - 1) * (int64_t)step + n <= N || W == 0,
+                 "sc_mt_fft: windows [%lld, %lld) exceed the series (N=%lld, n=%d, step=%d)", (long long)w0,
+                 (long long)(w0 + W), (long long)N, n, step);
+    SC_CHECK_ARG(n_freq_out >= 1 && n_freq_out <= nfft, "sc_mt_fft: n_freq_out %d outside [1, %d]", n_freq_out, nfft);
+    SC_CHECK_ARG(detrend >= 0 && detrend <= 2, "sc_mt_fft: unknown detrend mode %d", detrend);
+    SC_CHECK_ARG(layout == SC_LAYOUT_PLANAR || layout == SC_LAYOUT_REFERENCE, "sc_mt_fft: unknown layout %d", layout);
+    SC_CHECK_ARG(layout != SC_LAYOUT_PLANAR || (map && n_reduce > 0), "sc_mt_fft: planar layout needs map and n_reduce");
+    if (W == 0) return SC_OK;
+    MtParams p;
+    p.x = x; p.N = N; p.T = T; p.S = S; p.tapers = tapers; p.n = n; p.K = K; p.step = step;
+    p.w0 = w0; p.W = W; p.w_out0 = w_out0; p.nfft = nfft; p.detrend = detrend; p.scale = scale;
+    p.tw = reinterpret_cast<const cx<float>*>(twiddle);
+    p.layout = layout; p.nfo = n_freq_out;
+    if (map) p.map = ScMap{map[0], map[1], map[2], map[3], map[4], map[5]};
+    else p.map = ScMap{0, 0, 0, 0, 0, 0};
+    p.R = n_reduce; p.out = out; p.ws = nullptr;
+    if (sc_fft_make_plan(nfft, &p.plan)) {
+        sc_set_error("sc_mt_fft: cannot factorise nfft=%d", nfft);
+        return SC_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int ts = mt_pick_ts(n, nfft);
+    const int tsz = ts ? ts : 2;
+    const long long tiles = (S + tsz - 1) / tsz;
+    const long long total = W * T * tiles;
+    if (ts == 0) {
+        const int64_t need = (int64_t)kWsCtas * 2 * nfft * 8;
+        if (!workspace || workspace_bytes < need) {
+            sc_set_error("sc_mt_fft: window of %d samples (nfft %d) needs a %lld-byte workspace", n, nfft,
+                         (long long)need);
+            return SC_ERR_WORKSPACE;
+        }
+        p.ws = reinterpret_cast<cx<float>*>(workspace);
+        return mt_launch<2, true>(p, 0, total < kWsCtas ? total : kWsCtas, st);
+    }
+    const size_t smem = mt_smem_bytes(ts, n, nfft);
+    const long long maxgrid = 1LL << 30;
+    const long long grid = total < maxgrid ? total : maxgrid;
+    switch (ts) {
+        case 8: return mt_launch<8, false>(p, smem, grid, st);
+        case 4: return mt_launch<4, false>(p, smem, grid, st);
+        default: return mt_launch<2, false>(p, smem, grid, st);
+    }
+}
+
+extern "C" int sc_repack_coefficients(const void* coef_c64, int64_t W, int64_t T, int64_t K, int64_t nfft, int64_t S,
+                                      int n_freq_out, const int64_t* map, int64_t n_reduce, float* out,
+                                      void* stream) {
+    SC_CHECK_ARG(coef_c64 && out && map, "sc_repack_coefficients: null pointer");
+    SC_CHECK_ARG(W > 0 && T > 0 && K > 0 && nfft > 0 && S > 0 && n_reduce > 0, "sc_repack_coefficients: bad size");
+    SC_CHECK_ARG(n_freq_out >= 1 && n_freq_out <= nfft, "sc_repack_coefficients: n_freq_out out of range");
+    const long long total = W * T * K * (long long)n_freq_out * S;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sc_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    repack_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(coef_c64), W, T, K, nfft, S, n_freq_out,
+        ScMap{map[0], map[1], map[2], map[3], map[4], map[5]}, n_reduce, out);
+    SC_LAUNCH_OK();
+    return SC_OK;
+}

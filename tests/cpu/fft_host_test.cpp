@@ -1,0 +1,64 @@
+// Host build of the device FFT butterflies (tests only): runs every Stockham stage
+// sequentially so numpy can check the index arithmetic without a GPU.
+#include <vector>
+#include <cmath>
+#include "../../spectral_connectivity_b200/csrc/fft_device.cuh"
+
+template <typename R, int RADIX>
+static void pass(const cx<R>* src, cx<R>* dst, int n, int Ls, const cx<R>* tw, bool inv) {
+    for (int j = 0; j < n / RADIX; ++j) sc_fft_item<R, RADIX>(src, dst, j, n, Ls, tw, inv);
+}
+
+template <typename R>
+static int run(R* data, int n, int inverse, int force_generic) {
+    ScFftPlan plan;
+    if (sc_fft_make_plan(n, &plan)) return -1;
+    std::vector<cx<R>> a(n), b(n), tw(n);
+    for (int i = 0; i < n; ++i) {
+        a[i].x = data[2 * i];
+        a[i].y = data[2 * i + 1];
+        tw[i].x = (R)cos(-2.0 * M_PI * i / n);
+        tw[i].y = (R)sin(-2.0 * M_PI * i / n);
+    }
+    cx<R>* src = a.data();
+    cx<R>* dst = b.data();
+    int Ls = 1;
+    const bool inv = inverse != 0;
+    for (int s = 0; s < plan.nstages; ++s) {
+        const int r = plan.radix[s];
+        int rr = force_generic ? -1 : r;
+        switch (rr) {
+            case 2: pass<R, 2>(src, dst, n, Ls, tw.data(), inv); break;
+            case 3: pass<R, 3>(src, dst, n, Ls, tw.data(), inv); break;
+            case 4: pass<R, 4>(src, dst, n, Ls, tw.data(), inv); break;
+            case 5: pass<R, 5>(src, dst, n, Ls, tw.data(), inv); break;
+            case 7: pass<R, 7>(src, dst, n, Ls, tw.data(), inv); break;
+            case 8: pass<R, 8>(src, dst, n, Ls, tw.data(), inv); break;
+            case 10: pass<R, 10>(src, dst, n, Ls, tw.data(), inv); break;
+            case 11: pass<R, 11>(src, dst, n, Ls, tw.data(), inv); break;
+            case 13: pass<R, 13>(src, dst, n, Ls, tw.data(), inv); break;
+            default:
+                for (int it = 0; it < n; ++it) sc_fft_item_generic<R>(src, dst, it, r, n, Ls, tw.data(), inv);
+        }
+        Ls *= r;
+        std::swap(src, dst);
+    }
+    for (int i = 0; i < n; ++i) {
+        data[2 * i] = src[i].x;
+        data[2 * i + 1] = src[i].y;
+    }
+    return plan.nstages;
+}
+
+extern "C" int fft_host_f64(double* data, int n, int inverse, int force_generic) {
+    return run<double>(data, n, inverse, force_generic);
+}
+extern "C" int fft_host_f32(float* data, int n, int inverse, int force_generic) {
+    return run<float>(data, n, inverse, force_generic);
+}
+extern "C" int fft_plan(int n, int* radices) {
+    ScFftPlan plan;
+    if (sc_fft_make_plan(n, &plan)) return -1;
+    for (int i = 0; i < plan.nstages; ++i) radices[i] = plan.radix[i];
+    return plan.nstages;
+}

@@ -1,0 +1,61 @@
+"""CPU check of the device FFT butterflies/index math (g++ build of fft_device.cuh)."""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    out = os.path.join(tempfile.mkdtemp(), "libfft_host_test.so")
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-o", out,
+                           os.path.join(HERE, "cpu", "fft_host_test.cpp")])
+    return ctypes.CDLL(out)
+
+
+SIZES = [1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 16, 17, 20, 27, 30, 49, 61, 64, 100, 101, 120, 121,
+         128, 169, 250, 289, 500, 1000, 1001, 1008, 1024, 2 * 3 * 5 * 7 * 11, 7203]
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_fft_f64(lib, n, inverse):
+    rng = np.random.default_rng(n)
+    z = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    buf = np.ascontiguousarray(z.view(np.float64).copy())
+    st = lib.fft_host_f64(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n, inverse, 0)
+    assert st >= 0
+    ref = np.fft.ifft(z) * n if inverse else np.fft.fft(z)
+    got = buf.view(np.complex128)
+    assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) * max(1, np.log2(n + 1))
+
+
+@pytest.mark.parametrize("n", [12, 35, 100, 1000])
+def test_fft_generic_stage(lib, n):
+    rng = np.random.default_rng(n)
+    z = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    buf = np.ascontiguousarray(z.view(np.float64).copy())
+    lib.fft_host_f64(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n, 0, 1)
+    assert np.abs(buf.view(np.complex128) - np.fft.fft(z)).max() <= 1e-11 * np.abs(z).sum()
+
+
+@pytest.mark.parametrize("n", [120, 1000, 1008])
+def test_fft_f32(lib, n):
+    rng = np.random.default_rng(n)
+    z = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    buf = np.ascontiguousarray(z.view(np.float32).copy())
+    lib.fft_host_f32(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), n, 0, 0)
+    ref = np.fft.fft(z.astype(np.complex128))
+    assert np.abs(buf.view(np.complex64) - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_plan_1000(lib):
+    r = (ctypes.c_int * 32)()
+    assert lib.fft_plan(1000, r) == 3 and list(r[:3]) == [10, 10, 10]
+    assert lib.fft_plan(120, r) == 3 and list(r[:3]) == [10, 4, 3]
+    assert lib.fft_plan(101, r) == 1 and r[0] == 101

@@ -1,0 +1,296 @@
+"""GPU parity tests (run on the B200 box): CUDA path through the C ABI vs the oracle, the
+golden fixtures generated from the live reference, and the reference's own known answers.
+
+Tolerance contract (SURVEY.md section 8d / BASELINE.json north_star): identical shapes and NaN
+masks, scale-normalised max error <= 1e-5 and allclose(rtol=1e-5, atol=1e-5*max|ref|) -- fp32
+pipeline against the float64 reference.
+"""
+import numpy as np
+import pytest
+import torch
+from conftest import assert_parity, golden
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def sc():
+    import spectral_connectivity_b200 as sc
+    assert torch.cuda.is_available()
+    return sc
+
+
+# --------------------------------------------------------------------------- #
+# Multitaper.fft
+# --------------------------------------------------------------------------- #
+MT_KW = {
+    "whole": dict(time_halfbandwidth_product=2),
+    "sliding": dict(time_halfbandwidth_product=2, time_window_duration=0.4, time_window_step=0.2),
+    "linear": dict(time_halfbandwidth_product=3, time_window_duration=1.0, detrend_type="linear"),
+    "nodetrend": dict(time_halfbandwidth_product=3, time_window_duration=1.0, detrend_type=None),
+    "crop": dict(time_halfbandwidth_product=2, time_window_duration=1.0, n_fft_samples=64),
+    "pad": dict(time_halfbandwidth_product=2, time_window_duration=1.0, n_fft_samples=128),
+    "odd": dict(time_halfbandwidth_product=2, time_window_duration=1.0),
+    "prime": dict(time_halfbandwidth_product=2, time_window_duration=1.0, n_fft_samples=101),
+}
+
+
+@pytest.mark.parametrize("name", list(MT_KW))
+def test_multitaper_fft_golden(sc, name):
+    g = golden("multitaper_fft.npz")
+    fs = g[f"{name}_meta"][3]
+    m = sc.Multitaper(g[f"{name}_x"], sampling_frequency=fs, **MT_KW[name])
+    assert_parity(m.tapers, g[f"{name}_tapers"], 1e-9, "tapers")
+    got = m.fft().cpu().numpy()
+    assert got.dtype == np.complex64
+    assert_parity(got, g[f"{name}_fft"], TOL, name)
+
+
+def test_multitaper_fft_user_tapers_and_single_signal(sc):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((300, 3, 1))
+    taps = rng.standard_normal((100, 2))
+    m = sc.Multitaper(x, sampling_frequency=100.0, n_time_samples_per_window=100, tapers=taps)
+    ref = O.multitaper_fft(x, 100.0, taps, 100, 100, 100)
+    assert_parity(m.fft().cpu().numpy(), ref, TOL, "user tapers")
+
+
+def test_multitaper_fft_long_window_workspace_path(sc):
+    # window too long for shared memory -> global-workspace kernel
+    fs, n = 1000.0, 40000
+    x = O.synthetic_series(n, 1, 3, fs, seed=11)
+    m = sc.Multitaper(x, sampling_frequency=fs, time_halfbandwidth_product=2)
+    taps = O.dpss_tapers(n, 2, 3, fs)
+    ref = O.multitaper_fft(x, fs, taps, n, n, m.n_fft_samples)
+    assert_parity(m.fft().cpu().numpy(), ref, 2e-5, "long window")
+
+
+@pytest.mark.parametrize("shape", [(1000, 4, 8), (2000, 3, 17), (360, 2, 33)])
+def test_multitaper_fft_vs_oracle(sc, shape):
+    n_samples, n_trials, n_signals = shape
+    fs = 500.0
+    x = O.synthetic_series(n_samples, n_trials, n_signals, fs, seed=1)
+    dur = None if n_samples == 1000 else 0.24
+    m = sc.Multitaper(x, sampling_frequency=fs, time_halfbandwidth_product=2, time_window_duration=dur)
+    n, step, nfft = O.window_geometry(n_samples, fs, dur)
+    taps = O.dpss_tapers(n, 2, 3, fs)
+    ref = O.multitaper_fft(x, fs, taps, n, step, nfft)
+    assert_parity(m.fft().cpu().numpy(), ref, TOL, str(shape))
+
+
+# --------------------------------------------------------------------------- #
+# Connectivity measures vs golden (live reference output)
+# --------------------------------------------------------------------------- #
+GOLDEN_MEASURES = ["power", "coherency", "coherence_magnitude", "coherence_phase", "imaginary_coherence",
+                   "phase_locking_value", "phase_lag_index", "weighted_phase_lag_index",
+                   "debiased_squared_phase_lag_index", "debiased_squared_weighted_phase_lag_index",
+                   "pairwise_phase_consistency"]
+# measures with a removable singularity / cancellation get a looser scale-normalised bound
+LOOSE = {"coherence_phase": 2e-4, "debiased_squared_weighted_phase_lag_index": 2e-4,
+         "debiased_squared_phase_lag_index": 2e-5, "pairwise_phase_consistency": 2e-5}
+
+
+@pytest.mark.parametrize("et", list(O.EXPECTATION_AXES))
+def test_measures_from_coefficients_golden(sc, et):
+    g = golden("connectivity.npz")
+    c = sc.Connectivity(g["coef"], expectation_type=et)
+    got = c.compute(GOLDEN_MEASURES + ["expectation_cross_spectral_matrix"])
+    nf = g["coef"].shape[3] // 2 + 1
+    ref_csm = np.take(g[f"{et}__csm"], np.arange(nf), axis=-3)
+    assert_parity(got["expectation_cross_spectral_matrix"], ref_csm, TOL, "csm")
+    for name in GOLDEN_MEASURES:
+        ref = g[f"{et}__{name}"]
+        if name == "coherence_phase":  # +pi / -pi are the same angle
+            d = np.angle(np.exp(1j * (got[name] - ref)))
+            assert np.array_equal(np.isnan(d), np.isnan(ref))
+            assert np.nanmax(np.abs(d)) < LOOSE[name]
+            continue
+        assert_parity(got[name], ref, LOOSE.get(name, TOL), f"{et}/{name}")
+
+
+def test_measures_from_multitaper_golden(sc):
+    g = golden("connectivity.npz")
+    fs, nw, dur = g["meta"]
+    m = sc.Multitaper(g["x"], sampling_frequency=fs, time_halfbandwidth_product=nw, time_window_duration=dur)
+    c = sc.Connectivity.from_multitaper(m)
+    assert c.n_observations == 4 * 5
+    assert np.array_equal(c.frequencies, O.non_negative_frequencies(m.frequencies))
+    got = c.compute(GOLDEN_MEASURES + ["pairwise_spectral_granger_prediction"])
+    for name in GOLDEN_MEASURES:
+        if name == "coherence_phase":
+            continue
+        assert_parity(got[name], g[f"trials_tapers__{name}"], LOOSE.get(name, TOL), name)
+    assert_parity(got["pairwise_spectral_granger_prediction"],
+                  g["trials_tapers__pairwise_spectral_granger_prediction"], TOL, "granger")
+    # single-measure methods agree with the fused pass
+    assert_parity(c.coherence_magnitude(), got["coherence_magnitude"], 1e-7, "method")
+    assert_parity(c.weighted_phase_lag_index(), got["weighted_phase_lag_index"], 1e-7, "method")
+
+
+def test_two_sided_private_quantities(sc):
+    g = golden("connectivity.npz")
+    c = sc.Connectivity(g["coef"])
+    assert_parity(c._expectation_cross_spectral_matrix(), g["trials_tapers__csm"], TOL, "two-sided csm")
+    assert_parity(c._power, O.power(g["coef"]), TOL, "two-sided power")
+    unavg = c._cross_spectral_matrix
+    assert_parity(unavg, O.cross_spectral_matrix(g["coef"]), TOL, "un-averaged csm")
+
+
+def test_granger_from_coefficients_two_sided(sc):
+    g = golden("connectivity.npz")
+    c = sc.Connectivity(g["coef"])
+    got = c.pairwise_spectral_granger_prediction()
+    assert_parity(got, g["trials_tapers__pairwise_spectral_granger_prediction"], TOL, "granger two-sided")
+    sub = c.subset_pairwise_spectral_granger_prediction([[0, 2], [1, 3]])
+    ref = np.full_like(got, np.nan)
+    for i, j in ((0, 2), (1, 3)):
+        ref[..., i, j] = got[..., i, j]
+        ref[..., j, i] = got[..., j, i]
+    assert_parity(sub, ref, 1e-6, "subset granger")
+
+
+def test_wilson_golden(sc):
+    g = golden("wilson.npz")
+    got, iters, flags = sc.minimum_phase_decomposition(g["csm2"], return_info=True)
+    assert_parity(got, g["g2"], 1e-9, "wilson G")
+    _, ref_it = O.wilson(g["csm2"], return_iterations=True)
+    assert np.array_equal(iters, ref_it) and not flags.any()
+
+
+def test_wilson_reference_known_answer(sc):
+    # reference tests/test_minimum_phase_decomposition.py:96-119 uses a 1x1 system; embed two of
+    # them on the diagonal of a 2x2 problem (a decoupled system factorises entry-wise)
+    from scipy.signal import freqz_zpk
+    _, h1 = freqz_zpk(0.25, 0.50, 1.00, whole=True)
+    _, h2 = freqz_zpk(0.125, 0.25, 1.00, whole=True)
+    expected = np.zeros((2, h1.shape[0], 2, 2), dtype=complex)
+    expected[0, :, 0, 0], expected[0, :, 1, 1] = h1, h2
+    expected[1, :, 0, 0], expected[1, :, 1, 1] = h2, h1
+    csm = expected @ np.conj(np.swapaxes(expected, -1, -2))
+    got = sc.minimum_phase_decomposition(csm)
+    assert np.allclose(got, expected)
+    assert np.allclose(got @ np.conj(np.swapaxes(got, -1, -2)), csm)
+
+
+# --------------------------------------------------------------------------- #
+# the reference's own known answers (tests/test_connectivity.py:25-264)
+# --------------------------------------------------------------------------- #
+def _const_coef(shape, values):
+    coef = np.zeros(shape, dtype=complex)
+    coef[..., :] = values
+    return coef
+
+
+def test_reference_known_answers(sc):
+    two = [2 * np.exp(1j * np.pi / 2), 3 * np.exp(-1j * np.pi / 2)]
+    c = sc.Connectivity(_const_coef((1, 1, 1, 1, 2), two))
+    assert np.allclose(c.power(), [[[4, 9]]])
+    assert np.allclose(c._cross_spectral_matrix[0, 0, 0, 0], [[4, -6], [-6, 9]])
+    c = sc.Connectivity(_const_coef((1, 30, 1, 1, 2), two))
+    coh = c.coherency().squeeze()
+    assert np.allclose(np.abs(coh), [[np.nan, 1], [1, np.nan]], equal_nan=True)
+    assert np.allclose(np.abs(np.angle(coh)[[0, 1], [1, 0]]), np.pi)
+    same = [2 * np.exp(1j * 0), 3 * np.exp(1j * 0)]
+    c = sc.Connectivity(_const_coef((1, 30, 1, 1, 2), same))
+    assert np.allclose(c.imaginary_coherence().squeeze(), 0)
+    assert np.allclose(c.phase_lag_index().squeeze(), 0)
+    assert np.allclose(c.weighted_phase_lag_index().squeeze(), 0)
+    rng = np.random.default_rng(42)
+    coef = np.zeros((1, 30, 1, 1, 2), dtype=complex)
+    coef[..., 0] = rng.uniform(0.1, 2, (1, 30, 1, 1)) * np.exp(1j * np.pi / 2)
+    coef[..., 1] = rng.uniform(0.1, 2, (1, 30, 1, 1)) * np.exp(1j * np.pi / 4)
+    c = sc.Connectivity(coef)
+    assert np.allclose(c.phase_lag_index().squeeze(), [[0, 1], [-1, 0]])
+    assert np.allclose(c.phase_locking_value().squeeze()[0, 1], 1)
+    coef = _const_coef((1, 30, 1, 1, 2), [np.exp(1j * 3 * np.pi / 4), np.exp(1j * 5 * np.pi / 4)])
+    c = sc.Connectivity(coef)
+    assert np.allclose(c.phase_lag_index(), c.weighted_phase_lag_index())
+
+
+@pytest.mark.parametrize("et,shape", [("trials_tapers", (1, 4, 5)), ("trials", (1, 3, 4, 5)),
+                                      ("tapers", (1, 2, 4, 5))])
+def test_expectation_shapes(sc, et, shape):
+    # reference tests/test_connectivity.py:102-134 (n_fft=4 -> 3 non-negative bins)
+    c = sc.Connectivity(np.zeros((1, 2, 3, 4, 5), dtype=complex), expectation_type=et)
+    assert c.n_observations == {"trials_tapers": 6, "trials": 2, "tapers": 3}[et]
+    assert c.power().shape == shape[:-2] + (3, 5)
+    assert c._power.shape == shape
+
+
+# --------------------------------------------------------------------------- #
+# larger shapes vs the oracle (multiple CSM tiles, ragged sizes, chunked streaming)
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("n_signals,n_trials", [(70, 3), (130, 2), (1, 4)])
+def test_measures_vs_oracle_ragged(sc, n_signals, n_trials):
+    fs, n_samples = 250.0, 500
+    x = O.synthetic_series(n_samples, n_trials, n_signals, fs, seed=9)
+    m = sc.Multitaper(x, sampling_frequency=fs, time_halfbandwidth_product=2, time_window_duration=0.4)
+    c = sc.Connectivity.from_multitaper(m, max_chunk_bytes=1)  # one window per chunk
+    n, step, nfft = O.window_geometry(n_samples, fs, 0.4)
+    coef = O.multitaper_fft(x, fs, O.dpss_tapers(n, 2, 3, fs), n, step, nfft)
+    if n_signals == 1:
+        assert_parity(c.power(), O._nonneg(O.power(coef), -2), TOL, "power S=1")
+        return
+    got = c.compute(["coherence_magnitude", "weighted_phase_lag_index", "phase_locking_value"])
+    assert_parity(got["coherence_magnitude"], O.coherence_magnitude(coef, row_block=16), TOL, "coh")
+    assert_parity(got["weighted_phase_lag_index"], O.weighted_phase_lag_index(coef, row_block=16), 5e-5, "wpli")
+    assert_parity(got["phase_locking_value"], O.phase_locking_value(coef, row_block=16), TOL, "plv")
+
+
+def test_config1_full(sc):
+    """BASELINE config 1 end to end: 8 ch x 4 trials x 2 s @ 500 Hz, whole-series window."""
+    cfg = O.CONFIGS[1]
+    x = O.synthetic_series(cfg["N"], cfg["T"], cfg["S"], cfg["fs"], seed=20261017 + 1)
+    m = sc.Multitaper(x, sampling_frequency=cfg["fs"], time_halfbandwidth_product=cfg["NW"])
+    c = sc.Connectivity.from_multitaper(m)
+    got = c.compute(["coherence_magnitude", "pairwise_spectral_granger_prediction"])
+    n, step, nfft = O.window_geometry(cfg["N"], cfg["fs"])
+    coef = O.multitaper_fft(x, cfg["fs"], O.dpss_tapers(n, cfg["NW"], 3, cfg["fs"]), n, step, nfft)
+    assert_parity(got["coherence_magnitude"], O.coherence_magnitude(coef), TOL, "coh")
+    ref, its = O.pairwise_granger(O.expected_csm(coef), O.power(coef), return_iterations=True)
+    assert_parity(got["pairwise_spectral_granger_prediction"], ref, TOL, "granger")
+    gpu_it = c.last_granger_iterations.cpu().numpy()
+    assert np.abs(gpu_it.ravel() - np.array(its).ravel()).max() <= 1
+
+
+def test_granger_properties_full_size_window(sc):
+    """Size-independent properties at a BASELINE-config-4-sized window (1 s @ 1 kHz, 7 tapers):
+    NaN diagonal, non-negative values, finite off-diagonal, subset == full, and G G^H == S."""
+    fs = 1000.0
+    x = O.synthetic_series(2000, 16, 12, fs, seed=4)
+    m = sc.Multitaper(x, sampling_frequency=fs, time_halfbandwidth_product=4, time_window_duration=1.0)
+    c = sc.Connectivity.from_multitaper(m, output="torch")
+    gc = c.pairwise_spectral_granger_prediction()
+    assert gc.shape == (2, 501, 12, 12)
+    diag = torch.diagonal(gc, dim1=-2, dim2=-1)
+    assert torch.isnan(diag).all()
+    off = gc[~torch.isnan(gc)]
+    assert (off > 0).all() and torch.isfinite(off).all()
+    assert torch.isnan(gc).float().mean() < 0.2
+    assert int(c.last_granger_flags.sum()) == 0
+    sub = c.subset_pairwise_spectral_granger_prediction([[3, 7]])
+    assert torch.allclose(sub[..., 3, 7], gc[..., 3, 7], rtol=1e-6, atol=0, equal_nan=True)
+    assert torch.allclose(sub[..., 7, 3], gc[..., 7, 3], rtol=1e-6, atol=0, equal_nan=True)
+
+
+def test_linearity_and_scaling_properties(sc):
+    """Coherence is invariant to per-channel gain; power scales with gain^2 (size-independent)."""
+    fs = 1000.0
+    x = O.synthetic_series(3000, 4, 6, fs, seed=8)
+    gain = np.array([1.0, 2.0, 0.5, 3.0, 1.5, 0.25])
+    a = sc.Connectivity.from_multitaper(sc.Multitaper(x, fs, 3, time_window_duration=1.0))
+    b = sc.Connectivity.from_multitaper(sc.Multitaper(x * gain, fs, 3, time_window_duration=1.0))
+    assert_parity(b.coherence_magnitude(), a.coherence_magnitude(), 1e-5, "gain invariance")
+    assert_parity(b.power(), a.power() * gain ** 2, 1e-5, "power scaling")
+
+
+def test_zero_power_inputs_stay_finite(sc):
+    # reference tests/test_coherence_bounds.py:60-78
+    c = sc.Connectivity(np.zeros((1, 5, 1, 4, 3), dtype=complex))
+    coh = c.coherence_magnitude()
+    off = ~np.eye(3, dtype=bool)
+    assert np.isfinite(coh[..., off]).all() and (coh[..., off] == 0).all()

@@ -1,0 +1,149 @@
+"""CPU tests: host-side logic of the drop-in classes and the C-ABI surface (no compute)."""
+import ctypes
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+from conftest import ROOT, assert_parity, golden
+
+from spectral_connectivity_b200 import _lib
+from spectral_connectivity_b200._dpss import dpss_windows, make_tapers
+from spectral_connectivity_b200.transforms import EXPECTATION_AXES, Multitaper, expectation_map
+
+
+def test_geometry_bit_exact():
+    g = golden("geometry.npz")
+    for ci, row in enumerate(g["table"]):
+        n_samples, fs, dur, step = int(row[0]), row[1], row[2], row[3]
+        m = Multitaper(np.zeros((n_samples, 1, 1)), sampling_frequency=fs,
+                       time_window_duration=None if dur < 0 else dur,
+                       time_window_step=None if step < 0 else step, time_halfbandwidth_product=2)
+        assert m.n_time_samples_per_window == int(row[4])
+        assert m.n_time_samples_per_step == int(row[5])
+        assert m.n_fft_samples == int(row[6])
+        assert m.n_time_windows == int(row[7]) == len(m.time)
+        assert m.n_tapers == int(row[8])
+        assert np.array_equal(m.time, g[f"time_{ci}"])
+        assert np.array_equal(m.frequencies, g[f"freq_{ci}"])
+
+
+def test_tapers_match_reference():
+    g = golden("tapers.npz")
+    for key in g.files:
+        if key.startswith("tapers_"):
+            _, n, nw, k = key.split("_")
+            t, e = dpss_windows(int(n), float(nw), int(k), is_low_bias=False)
+            assert_parity(t, g[key], 1e-10, key)
+            assert_parity(e, g["eig_" + key[len("tapers_"):]], 1e-10, key)
+            assert np.allclose((t ** 2).sum(axis=1), 1.0)
+    t, _ = dpss_windows(64, 1.5, 4, is_low_bias=True)
+    assert_parity(t, g["lowbias_64_1.5_4"], 1e-10, "lowbias")
+    assert make_tapers(64, 100.0, 2.0, 3).shape == (64, 3)
+
+
+def test_multitaper_properties():
+    # mirrors reference tests/test_transforms.py:62-229
+    m = Multitaper(np.zeros((100, 1, 1)), sampling_frequency=1000, time_halfbandwidth_product=3)
+    assert m.n_tapers == 5 and m.n_time_samples_per_window == 100 and m.n_fft_samples == 100
+    assert m.time_window_duration == 0.1 and m.time_window_step == 0.1
+    assert m.nyquist_frequency == 500 and m.n_signals == 1 and m.n_trials == 1
+    assert m.frequency_resolution == pytest.approx(60.0)
+    m = Multitaper(np.zeros((100, 1, 1)), n_fft_samples=5)
+    assert m.n_fft_samples == 5 and len(m.frequencies) == 5
+    m = Multitaper(np.zeros((100, 1, 1)), sampling_frequency=1000, time_window_duration=0.02,
+                   time_window_step=0.01, start_time=2.0)
+    assert m.n_time_samples_per_step == 10 and m.n_time_windows == 9
+    assert np.allclose(m.time, 2.0 + np.arange(9) * 0.01)
+    m = Multitaper(np.zeros((23, 1, 1)), n_time_samples_per_window=8, n_time_samples_per_step=3, n_tapers=2)
+    assert m.n_time_windows == 6 and m.n_tapers == 2
+    custom = np.ones((8, 2))
+    m = Multitaper(np.zeros((23, 1, 1)), n_time_samples_per_window=8, tapers=custom)
+    assert np.array_equal(m.tapers, custom)
+
+
+def test_multitaper_validation():
+    with pytest.raises(ValueError, match="3D"):
+        Multitaper(np.zeros(10))
+    with pytest.raises(ValueError, match="3D"):
+        Multitaper(np.zeros((10, 2)))
+    with pytest.raises(ValueError, match="sampling_frequency"):
+        Multitaper(np.zeros((10, 1, 1)), sampling_frequency=0)
+    with pytest.raises(ValueError, match="time_halfbandwidth_product"):
+        Multitaper(np.zeros((10, 1, 1)), time_halfbandwidth_product=0.5)
+    with pytest.raises(ValueError, match="time_window_duration"):
+        Multitaper(np.zeros((10, 1, 1)), time_window_duration=-1)
+    with pytest.raises(ValueError, match="time_window_step"):
+        Multitaper(np.zeros((10, 1, 1)), time_window_step=0)
+    with pytest.raises(ValueError, match="trend"):
+        Multitaper(np.zeros((10, 1, 1)), detrend_type="quadratic")
+    with pytest.warns(UserWarning, match="NaN"):
+        Multitaper(np.full((10, 1, 1), np.nan))
+    with pytest.warns(UserWarning, match="transposed"):
+        Multitaper(np.zeros((3, 1, 8)))
+    with pytest.warns(UserWarning, match="unusually large"):
+        Multitaper(np.zeros((100, 1, 1)), time_halfbandwidth_product=11)
+    with pytest.warns(UserWarning, match="gaps"):
+        Multitaper(np.zeros((100, 1, 1)), sampling_frequency=100, time_window_duration=0.1, time_window_step=0.2)
+
+
+@pytest.mark.parametrize("et", list(EXPECTATION_AXES))
+def test_expectation_map_matches_numpy_mean(et):
+    w, t, k = 3, 4, 5
+    mapping, kept, nb, nr = expectation_map((w, t, k), et)
+    vals = np.random.default_rng(0).standard_normal((w, t, k))
+    acc = np.zeros(nb)
+    cnt = np.zeros(nb)
+    seen = set()
+    for iw in range(w):
+        for it in range(t):
+            for ik in range(k):
+                b = iw * mapping[0] + it * mapping[1] + ik * mapping[2]
+                r = iw * mapping[3] + it * mapping[4] + ik * mapping[5]
+                assert 0 <= b < nb and 0 <= r < nr and (b, r) not in seen
+                seen.add((b, r))
+                acc[b] += vals[iw, it, ik]
+                cnt[b] += 1
+    assert len(seen) == w * t * k and nb * nr == w * t * k
+    ref = vals.mean(axis=EXPECTATION_AXES[et])
+    assert np.allclose((acc / cnt).reshape(kept if kept else ()), ref)
+
+
+def test_connectivity_validation_without_gpu():
+    from spectral_connectivity_b200 import Connectivity
+    with pytest.raises(ValueError, match="5-dimensional"):
+        Connectivity(np.zeros((2, 2, 2), dtype=complex))
+    with pytest.raises(ValueError, match="Did you mean 'trials_tapers'"):
+        Connectivity(np.zeros((1, 1, 1, 1, 2), dtype=complex), expectation_type="tapers_trials")
+    with pytest.raises(ValueError, match="Invalid expectation_type"):
+        Connectivity(np.zeros((1, 1, 1, 1, 2), dtype=complex), expectation_type="bogus")
+
+
+def test_abi_exports_every_declared_symbol():
+    """The shared library loads and exports every function include/sc_b200.h declares."""
+    header = open(os.path.join(ROOT, "include", "sc_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(sc_[a-z0-9_]+)\s*\(", body))
+    assert {"sc_mt_fft", "sc_csm", "sc_power", "sc_pairwise_epilogue", "sc_wilson2",
+            "sc_granger_pairwise", "sc_repack_coefficients"} <= declared
+    assert os.path.exists(_lib.LIB_PATH), "build the library first (__graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in sc_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    loaded = _lib.load()
+    assert loaded.sc_version() >= 100
+    assert loaded.sc_wilson_workspace_bytes(1000) > 0
+    assert loaded.sc_mt_fft_workspace_bytes(1000, 1000) == 0
+    assert loaded.sc_mt_fft_workspace_bytes(60000, 60000) > 0
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "spectral_connectivity_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "/root/reference" not in src, f
