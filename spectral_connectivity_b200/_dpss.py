@@ -10,6 +10,7 @@ reference so the tapers agree to ~1e-11.
 """
 from __future__ import annotations
 
+import functools
 import logging
 
 import numpy as np
@@ -68,8 +69,17 @@ def dpss_windows(n_time_samples_per_window, time_halfbandwidth_product, n_tapers
     return tapers, eigenvalues
 
 
+@functools.lru_cache(maxsize=32)
+def _cached_tapers(n, fs, nw, k, low_bias):
+    tapers, _ = dpss_windows(n, nw, k, low_bias)
+    out = tapers.T * np.sqrt(fs)
+    out.setflags(write=False)
+    return out
+
+
 def make_tapers(n_time_samples_per_window, sampling_frequency, time_halfbandwidth_product, n_tapers,
                 is_low_bias=True):
-    """(n, K) tapers scaled by sqrt(fs) (transforms.py:1408-1440)."""
-    tapers, _ = dpss_windows(n_time_samples_per_window, time_halfbandwidth_product, n_tapers, is_low_bias)
-    return tapers.T * np.sqrt(sampling_frequency)
+    """(n, K) tapers scaled by sqrt(fs) (transforms.py:1408-1440); cached per parameter set
+    (the reference recomputes them for every Multitaper instance)."""
+    return _cached_tapers(int(n_time_samples_per_window), float(sampling_frequency),
+                          float(time_halfbandwidth_product), int(n_tapers), bool(is_low_bias))

@@ -42,6 +42,52 @@ M_PLV, M_PPC, M_PLI, M_WPLI, M_DPLI2, M_DWPLI2 = 4, 5, 6, 7, 8, 9
 FLAG_NOT_CONVERGED, FLAG_NOT_SPD = 1, 2
 
 _lib = None
+LAUNCHES = 0  # kernels launched through the ABI by this process (every checked call launches one)
+
+
+class StageTimer:
+    """Optional per-stage CUDA-event timing (bench.py): events are recorded on the current
+    stream around each ABI call; ``totals()`` synchronises and sums milliseconds per stage."""
+
+    def __init__(self):
+        self.events = []
+
+    def span(self, name):
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.events.append((name, a, b))
+        return a, b
+
+    def totals(self):
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.events:
+            ms, n = out.get(name, (0.0, 0))
+            out[name] = (ms + a.elapsed_time(b), n + 1)
+        return out
+
+
+TIMER = None  # set to a StageTimer to collect per-kernel times
+
+
+class timed:
+    """with timed("stage"): <one ABI call>"""
+
+    def __init__(self, name):
+        self.name = name
+        self.ev = None
+
+    def __enter__(self):
+        if TIMER is not None:
+            self.ev = TIMER.span(self.name)
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record()
+        return False
 
 
 class NativeLibraryError(ImportError):
@@ -69,6 +115,8 @@ def load():
 
 
 def check(rc, what=""):
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         msg = load().sc_last_error()
         raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

@@ -168,7 +168,11 @@ class Connectivity:
     def _finish(self, t):
         if self._output == "torch":
             return t
-        return t.cpu().numpy()
+        # device -> host through a pinned staging tensor (torch caches pinned allocations)
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()
 
     # ---- streaming engine ----------------------------------------------------------
     def _chunks(self, n_freq):
@@ -276,29 +280,33 @@ class Connectivity:
             power = csm = None
             if need_power:
                 power = torch.empty((nb, n_freq, n_sig), dtype=torch.float32, device=dev)
-                _lib.check(lib.sc_power(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.ptr(power), st), "sc_power")
+                with _lib.timed("power"):
+                    _lib.check(lib.sc_power(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.ptr(power), st), "sc_power")
                 self._allreduce(power)
                 if "power" in out:
                     out["power"][b0:b1] = power
             if "csm" in needs:
                 csm = torch.empty((nb, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
-                _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(csm), st),
-                           "sc_csm")
+                with _lib.timed("csm"):
+                    _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(csm), st),
+                               "sc_csm")
                 self._allreduce(csm)
                 if "expectation_cross_spectral_matrix" in out:
                     out["expectation_cross_spectral_matrix"][b0:b1] = csm
             plv = pli = None
             if "plv" in needs:
                 plv = torch.empty((nb, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
-                _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_PLV, _lib.ptr(plv), st),
-                           "sc_csm[plv]")
+                with _lib.timed("plv"):
+                    _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_PLV, _lib.ptr(plv), st),
+                               "sc_csm[plv]")
                 self._allreduce(plv)
                 if "_phase_locking_value" in out:
                     out["_phase_locking_value"][b0:b1] = plv
             if "pli" in needs:
                 pli = torch.empty((4, nb, n_freq, n_sig, n_sig), dtype=torch.float32, device=dev)
-                _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_PLI, _lib.ptr(pli), st),
-                           "sc_csm[pli]")
+                with _lib.timed("pli"):
+                    _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_PLI, _lib.ptr(pli), st),
+                               "sc_csm[pli]")
                 self._allreduce(pli)
             del xp
             for name in measures:
@@ -307,18 +315,21 @@ class Connectivity:
                 src_kind, code, _ = _PAIRWISE[name]
                 src = {"csm": csm, "plv": plv, "pli": pli}[src_kind]
                 dst = out[name][b0:b1]
-                _lib.check(lib.sc_pairwise_epilogue(code, _lib.ptr(src), _lib.ptr(power) if src_kind == "csm" else None,
-                                                    nb, n_freq, n_sig, float(self.n_observations), _lib.ptr(dst), st),
-                           f"sc_pairwise_epilogue[{name}]")
+                with _lib.timed("epilogue"):
+                    _lib.check(lib.sc_pairwise_epilogue(code, _lib.ptr(src),
+                                                        _lib.ptr(power) if src_kind == "csm" else None, nb, n_freq,
+                                                        n_sig, float(self.n_observations), _lib.ptr(dst), st),
+                               f"sc_pairwise_epilogue[{name}]")
             if want_granger:
                 it_c = torch.zeros((n_pairs, nb), dtype=torch.int32, device=dev)
                 fl_c = torch.zeros((n_pairs, nb), dtype=torch.int32, device=dev)
                 dst = out["pairwise_spectral_granger_prediction"][b0:b1]
-                rc = lib.sc_granger_pairwise(_lib.ptr(csm), _lib.ptr(power), nb, n_freq, nfft, 1 if self._hermitian else 0,
-                                             n_sig, _lib.ptr(pair_t), n_pairs, float(tolerance), int(max_iterations),
-                                             _lib.ptr(tw128), _lib.ptr(dst), _lib.ptr(it_c), _lib.ptr(fl_c),
-                                             _lib.ptr(gr_ws), ws_bytes, st)
-                _lib.check(rc, "sc_granger_pairwise")
+                with _lib.timed("granger"):
+                    rc = lib.sc_granger_pairwise(_lib.ptr(csm), _lib.ptr(power), nb, n_freq, nfft,
+                                                 1 if self._hermitian else 0, n_sig, _lib.ptr(pair_t), n_pairs,
+                                                 float(tolerance), int(max_iterations), _lib.ptr(tw128), _lib.ptr(dst),
+                                                 _lib.ptr(it_c), _lib.ptr(fl_c), _lib.ptr(gr_ws), ws_bytes, st)
+                    _lib.check(rc, "sc_granger_pairwise")
                 it_all[:, b0:b1] = it_c
                 fl_all[:, b0:b1] = fl_c
 

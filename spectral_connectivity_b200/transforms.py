@@ -276,12 +276,14 @@ class Multitaper:
         n, step, nfft = self.n_time_samples_per_window, self.n_time_samples_per_step, self.n_fft_samples
         ws_bytes = lib.sc_mt_fft_workspace_bytes(n, nfft)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device) if ws_bytes else None
-        rc = lib.sc_mt_fft(_lib.ptr(self.time_series), n_samples, n_trials, n_signals, _lib.ptr(taps), n,
-                           taps.shape[0], step, w0, n_win, w_out0, nfft, _lib.DETREND[self.detrend_type],
-                           1.0 / float(self.sampling_frequency), _lib.ptr(self._twiddle()), layout,
-                           n_freq_out, _lib.map6(mapping) if mapping is not None else None, n_reduce,
-                           _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
-        _lib.check(rc, "sc_mt_fft")
+        tw = self._twiddle()
+        with _lib.timed("mt_fft"):
+            rc = lib.sc_mt_fft(_lib.ptr(self.time_series), n_samples, n_trials, n_signals, _lib.ptr(taps), n,
+                               taps.shape[0], step, w0, n_win, w_out0, nfft, _lib.DETREND[self.detrend_type],
+                               1.0 / float(self.sampling_frequency), _lib.ptr(tw), layout,
+                               n_freq_out, _lib.map6(mapping) if mapping is not None else None, n_reduce,
+                               _lib.ptr(out), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+            _lib.check(rc, "sc_mt_fft")
         return out
 
     def fft(self):
