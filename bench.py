@@ -29,6 +29,7 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # name: N, T, S, fs, NW, window seconds
     "cfg4": dict(N=60_000, T=64, S=256, fs=1000.0, NW=4.0, duration=1.0),
+    "cfg4w4": dict(N=4_000, T=64, S=256, fs=1000.0, NW=4.0, duration=1.0),  # 4 windows of cfg4 (profiling)
     "cfg3": dict(N=30_000, T=32, S=128, fs=1000.0, NW=4.0, duration=1.0),
     "cfg2": dict(N=10_000, T=16, S=64, fs=1000.0, NW=3.0, duration=1.0),
     "cfg1": dict(N=1000, T=4, S=8, fs=500.0, NW=2.0, duration=None),
@@ -128,7 +129,7 @@ def run_reference(args, wl_name, wl):
 
 def workload_config(wl_name, wl, n_gpus):
     n, n_win, nfft, fnn = geometry(wl)
-    return {"workload": f"BASELINE configs[{wl_name[-1]}]: {wl['S']}-channel x {wl['T']}-trial x "
+    return {"workload": f"BASELINE configs[{wl_name[3]}]{' (reduced windows)' if len(wl_name) > 4 else ''}: {wl['S']}-channel x {wl['T']}-trial x "
                         f"{wl['N'] / wl['fs']:.0f} s @ {wl['fs']:.0f} Hz, {int(2 * wl['NW'] - 1)} tapers, "
                         f"{n_win} windows of {n} samples, nfft {nfft}; coherence_magnitude + "
                         "pairwise_spectral_granger_prediction (Wilson tol 1e-8, <=60 it)",

@@ -260,7 +260,9 @@ __device__ __forceinline__ void sc_cta_fft_pass(const cx<R>* src, cx<R>* dst, in
 // nbatch FFTs of length plan.n at a + b*bstride, ping-pong with buffer b (same layout).
 // All threads of the CTA must call it; returns the buffer that holds the result.
 // Unnormalised in both directions.
-template <typename R>
+// LEAN = true routes the register-hungry prime radices (7, 11, 13) through the runtime-radix
+// path so that kernels compiled under a tight register cap (fp64 Wilson) do not spill.
+template <typename R, bool LEAN = false>
 __device__ cx<R>* sc_cta_fft(cx<R>* a, cx<R>* b, int nbatch, int bstride, const ScFftPlan& plan,
                              const cx<R>* tw, bool inv) {
     const int n = plan.n;
@@ -269,7 +271,7 @@ __device__ cx<R>* sc_cta_fft(cx<R>* a, cx<R>* b, int nbatch, int bstride, const 
     int Ls = 1;
     for (int s = 0; s < plan.nstages; ++s) {
         const int r = plan.radix[s];
-        switch (r) {
+        switch ((LEAN && (r == 7 || r == 11 || r == 13)) ? -1 : r) {
             case 2: sc_cta_fft_pass<R, 2>(src, dst, nbatch, bstride, n, Ls, tw, inv); break;
             case 3: sc_cta_fft_pass<R, 3>(src, dst, nbatch, bstride, n, Ls, tw, inv); break;
             case 4: sc_cta_fft_pass<R, 4>(src, dst, nbatch, bstride, n, Ls, tw, inv); break;

@@ -1,0 +1,272 @@
+// Pairwise spectral Granger for REAL time series (conjugate-symmetric spectra) -- the
+// from_multitaper hot path.  Same mathematics as wilson.cu (minimum_phase_decomposition.py:227-322,
+// connectivity.py:2282-2340) but exploiting S(-f) = conj S(f):
+//
+//  * only the nfft/2+1 non-negative bins are ever evaluated; the 2x2 factor G(f) and the three
+//    independent entries of S(f) live in REGISTERS (each thread owns FPT frequencies), so the
+//    only shared-memory traffic is the FFT ping-pong buffer;
+//  * the linear predictor B = G^-1 S G^-H + I is Hermitian with real even diagonal, so its inverse
+//    transform is real: c00 + i*c11 come out of ONE complex FFT, c01 out of a second
+//    (c10[k] = c01[-k]); the four causal sequences go back through TWO complex FFTs packed two
+//    real sequences each.  4 complex FFTs per iteration instead of the reference's 8;
+//  * the Granger epilogue (transfer function, noise covariance, log ratio) is evaluated from the
+//    registers and written straight into the (B, Fnn, S, S) output.
+#include "wilson_common.cuh"
+
+namespace {
+
+using namespace scw;
+
+template <typename R> struct RealOps;
+template <> struct RealOps<double> {
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+};
+template <> struct RealOps<float> {
+    static __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
+};
+
+// One Wilson iteration on the half spectrum held in registers.  Returns max |dG|^2 of this thread.
+template <typename R, int FPT>
+__device__ __forceinline__ R herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[FPT], cx<R> (&g10)[FPT],
+                                            cx<R> (&g11)[FPT], const float (&s00)[FPT], const float (&s11)[FPT],
+                                            const float2 (&s01)[FPT], R sscale, cx<R>* ZA, cx<R>* ZB,
+                                            const ScFftPlan& plan, const cx<R>* tw, int N, int fnn) {
+    // ---- linear predictor (mpd.py:218-224), Hermitian: b00, b11 real, b10 = conj(b01) ----
+#pragma unroll
+    for (int q = 0; q < FPT; ++q) {
+        const int f = threadIdx.x + q * kThreads;
+        if (f < fnn) {
+            const cx<R> det = csub(cmul(g00[q], g11[q]), cmul(g01[q], g10[q]));
+            const R dn = RealOps<R>::rcp(det.x * det.x + det.y * det.y);
+            const cx<R> idet = cmake<R>(det.x * dn, -det.y * dn);
+            const cx<R> u0 = cmul(g11[q], idet), u1 = cmul(g01[q], idet);   // row 0 of G^-1 = (u0, -u1)
+            const cx<R> v0 = cmul(g10[q], idet), v1 = cmul(g00[q], idet);   // row 1 of G^-1 = (-v0, v1)
+            const R a = (R)s00[q] * sscale, d = (R)s11[q] * sscale;
+            const cx<R> c = cmake<R>((R)s01[q].x * sscale, (R)s01[q].y * sscale);
+            // M = Ginv S Ginv^H with rows r0 = (u0, -u1), r1 = (-v0, v1)
+            // t = r S : t0 = r.x*a + r.y*conj(c), t1 = r.x*c + r.y*d
+            const cx<R> cc = cconj(c);
+            const cx<R> t00 = csub(cscale(u0, a), cmul(u1, cc));
+            const cx<R> t01 = csub(cmul(u0, c), cscale(u1, d));
+            const cx<R> t10 = csub(cmul(v1, cc), cscale(v0, a));
+            const cx<R> t11 = csub(cscale(v1, d), cmul(v0, c));
+            // M00 = t0 . conj(r0), M11 = t1 . conj(r1), M01 = t0 . conj(r1)
+            const R b00 = (t00.x * u0.x + t00.y * u0.y) - (t01.x * u1.x + t01.y * u1.y) + (R)1;
+            const R b11 = (t11.x * v1.x + t11.y * v1.y) - (t10.x * v0.x + t10.y * v0.y) + (R)1;
+            // t0 . conj(r1) = -t00*conj(v0) + t01*conj(v1)
+            const cx<R> b01 = cmake<R>(-(t00.x * v0.x + t00.y * v0.y) + (t01.x * v1.x + t01.y * v1.y),
+                                       -(t00.y * v0.x - t00.x * v0.y) + (t01.y * v1.x - t01.x * v1.y));
+            const int fm = f == 0 ? 0 : N - f;
+            ZA[f] = cmake<R>(b00, b11);
+            ZA[fm] = cmake<R>(b00, b11);
+            ZA[N + fm] = cconj(b01);
+            ZA[N + f] = b01;  // last: for f == fm (DC, Nyquist) the imaginary part is ~0 either way
+        }
+    }
+    __syncthreads();
+    // ---- plus operator (mpd.py:129-142) on the real sequences, packed for the forward FFTs ----
+    cx<R>* c = sc_cta_fft<R, true>(ZA, ZB, 2, N, plan, tw, true);
+    cx<R>* o = (c == ZA) ? ZB : ZA;
+    const R inv_n = (R)1 / (R)N;
+    const int kcut = (N + 1) / 2;
+    for (int k = threadIdx.x; k < N; k += kThreads) {
+        cx<R> y1 = cmake<R>((R)0, (R)0), y2 = y1;
+        if (k < kcut) {
+            const R w = k == 0 ? (R)0.5 * inv_n : inv_n;
+            const cx<R> z1 = c[k];                  // c00[k] + i c11[k]
+            const R c01 = c[N + k].x;
+            const R c10 = k == 0 ? (R)0 : c[N + (N - k)].x;  // c10[k] = c01[-k]; zeroed at lag 0
+            y1 = cmake<R>(z1.x * w, c01 * w);       // p00 + i p01
+            y2 = cmake<R>(c10 * w, z1.y * w);       // p10 + i p11
+        }
+        o[k] = y1;
+        o[N + k] = y2;
+    }
+    __syncthreads();
+    const cx<R>* Q = sc_cta_fft<R, true>(o, c, 2, N, plan, tw, false);
+    // ---- G <- G P (mpd.py:305-307) ----
+    R err2 = (R)0;
+#pragma unroll
+    for (int q = 0; q < FPT; ++q) {
+        const int f = threadIdx.x + q * kThreads;
+        if (f < fnn) {
+            const int fm = f == 0 ? 0 : N - f;
+            const cx<R> a1 = Q[f], m1 = Q[fm], a2 = Q[N + f], m2 = Q[N + fm];
+            const R h = (R)0.5;
+            const cx<R> p00 = cmake<R>(h * (a1.x + m1.x), h * (a1.y - m1.y));
+            const cx<R> p01 = cmake<R>(h * (a1.y + m1.y), h * (m1.x - a1.x));
+            const cx<R> p10 = cmake<R>(h * (a2.x + m2.x), h * (a2.y - m2.y));
+            const cx<R> p11 = cmake<R>(h * (a2.y + m2.y), h * (m2.x - a2.x));
+            const cx<R> n00 = cadd(cmul(g00[q], p00), cmul(g01[q], p10));
+            const cx<R> n01 = cadd(cmul(g00[q], p01), cmul(g01[q], p11));
+            const cx<R> n10 = cadd(cmul(g10[q], p00), cmul(g11[q], p10));
+            const cx<R> n11 = cadd(cmul(g10[q], p01), cmul(g11[q], p11));
+            cx<R> dd;
+            dd = csub(n00, g00[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
+            dd = csub(n01, g01[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
+            dd = csub(n10, g10[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
+            dd = csub(n11, g11[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
+            g00[q] = n00; g01[q] = n01; g10[q] = n10; g11[q] = n11;
+        }
+    }
+    return err2;
+}
+
+template <int FPT>
+__global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[4 * kWarps];
+    const int N = p.nfft;
+    const int fnn = N / 2 + 1;
+    cd* ZA = reinterpret_cast<cd*>(smem_raw);
+    cd* ZB = ZA + 2 * (size_t)N;
+    const long long npairs = p.n_pairs;
+    const long long nprob = p.B * npairs;
+    const float fnan = __int_as_float(0x7fc00000);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    for (long long prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
+        const long long b = prob / npairs;
+        const long long pk = prob % npairs;
+        int pi, pj;
+        if (p.pairs) {
+            pi = p.pairs[2 * pk];
+            pj = p.pairs[2 * pk + 1];
+        } else {
+            decode_pair(pk, p.S, pi, pj);
+        }
+        // ---- load the three independent entries of S(f), f = 0..nfft/2 ----------
+        float s00[FPT], s11[FPT];
+        float2 s01[FPT];
+        double a[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < FPT; ++q) {
+            const int f = threadIdx.x + q * kThreads;
+            s00[q] = 0.f; s11[q] = 0.f; s01[q] = make_float2(0.f, 0.f);
+            if (f < fnn) {
+                const float2* m = reinterpret_cast<const float2*>(p.csm) + ((size_t)b * p.F + f) * p.S * p.S;
+                s00[q] = __ldg(&m[(size_t)pi * p.S + pi]).x;
+                s11[q] = __ldg(&m[(size_t)pj * p.S + pj]).x;
+                s01[q] = __ldg(&m[(size_t)pi * p.S + pj]);
+                const double w = (f == 0 || 2 * f == N) ? 1.0 : 2.0;  // bins f and nfft-f
+                a[0] += w * s00[q]; a[1] += w * s01[q].x; a[2] += w * s11[q];
+            }
+        }
+        block_sum<3>(a, red);
+        // ---- Cholesky of the real lag-0 covariance, G0 = L^T (mpd.py:75-77) ----
+        const double a00 = a[0] / N, a10 = a[1] / N, a11 = a[2] / N;
+        const double l00 = sqrt(a00), l10 = a10 / l00, d11 = a11 - l10 * l10, l11 = sqrt(d11);
+        int flag = 0, it_done = 0;
+        if (!(a00 > 0.0) || !(d11 > 0.0) || !isfinite(l00) || !isfinite(l11)) flag = SC_FLAG_NOT_SPD;
+        cd g00[FPT], g01[FPT], g10[FPT], g11[FPT];
+#pragma unroll
+        for (int q = 0; q < FPT; ++q) {
+            g00[q] = cmake<double>(l00, 0.0); g01[q] = cmake<double>(l10, 0.0);
+            g10[q] = cmake<double>(0.0, 0.0); g11[q] = cmake<double>(l11, 0.0);
+        }
+        if (!flag) {
+            bool converged = false;
+            for (int it = 0; it < p.max_iter && !converged; ++it) {
+                const double e2 = herm_iteration<double, FPT>(g00, g01, g10, g11, s00, s11, s01, 1.0, ZA, ZB, p.plan,
+                                                              p.tw, N, fnn);
+                const double err = sqrt(block_max(e2, red));  // also fences ZA/ZB reuse
+                it_done = it + 1;
+                converged = err < p.tol;
+            }
+            if (!converged) flag |= SC_FLAG_NOT_CONVERGED;
+        }
+        if (threadIdx.x == 0) {
+            if (p.iters) p.iters[pk * p.B + b] = it_done;
+            if (p.flags) p.flags[pk * p.B + b] = flag;
+        }
+        float* out = reinterpret_cast<float*>(p.out);
+        if (flag & SC_FLAG_NOT_SPD) {
+            for (int f = threadIdx.x; f < fnn; f += kThreads) {
+                float* m = out + ((size_t)b * fnn + f) * p.S * p.S;
+                m[(size_t)pi * p.S + pj] = fnan;
+                m[(size_t)pj * p.S + pi] = fnan;
+            }
+            continue;
+        }
+        // ---- Granger epilogue (connectivity.py:1705-1709, 1739-1748, 1847-1848, 1773-1779) ----
+        double h[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < FPT; ++q) {
+            const int f = threadIdx.x + q * kThreads;
+            if (f < fnn) {
+                const double w = (f == 0 || 2 * f == N) ? 1.0 : 2.0;
+                h[0] += w * g00[q].x; h[1] += w * g01[q].x; h[2] += w * g10[q].x; h[3] += w * g11[q].x;
+            }
+        }
+        block_sum<4>(h, red);
+        const double h00 = h[0] / N, h01 = h[1] / N, h10 = h[2] / N, h11 = h[3] / N;
+        const double lam = kTikhonov * (h00 * h00 + h01 * h01 + h10 * h10 + h11 * h11) * 0.25;
+        const double m00 = h00 + lam, m11 = h11 + lam;
+        const double mdet = m00 * m11 - h01 * h10;
+        const double v00 = m11 / mdet, v01 = -h01 / mdet, v10 = -h10 / mdet, v11 = m00 / mdet;
+        const double c00 = h00 * h00 + h01 * h01, c01 = h00 * h10 + h01 * h11, c11 = h10 * h10 + h11 * h11;
+        const double r01 = c11 - c01 * c01 / c00;
+        const double r10 = c00 - c01 * c01 / c11;
+#pragma unroll
+        for (int q = 0; q < FPT; ++q) {
+            const int f = threadIdx.x + q * kThreads;
+            if (f < fnn) {
+                const cd t01 = cmake<double>(g00[q].x * v01 + g01[q].x * v11, g00[q].y * v01 + g01[q].y * v11);
+                const cd t10 = cmake<double>(g10[q].x * v00 + g11[q].x * v10, g10[q].y * v00 + g11[q].y * v10);
+                const double pw_i = __ldg(&p.power[((size_t)b * p.F + f) * p.S + pi]);
+                const double pw_j = __ldg(&p.power[((size_t)b * p.F + f) * p.S + pj]);
+                double in01 = pw_i - r01 * (t01.x * t01.x + t01.y * t01.y);
+                double in10 = pw_j - r10 * (t10.x * t10.x + t10.y * t10.y);
+                if (in01 == 0.0) in01 = kEps64;
+                if (in10 == 0.0) in10 = kEps64;
+                double gc01 = log(pw_i) - log(in01);
+                double gc10 = log(pw_j) - log(in10);
+                if (gc01 <= 0.0) gc01 = qnan;
+                if (gc10 <= 0.0) gc10 = qnan;
+                float* m = out + ((size_t)b * fnn + f) * p.S * p.S;
+                m[(size_t)pi * p.S + pj] = (float)gc01;
+                m[(size_t)pj * p.S + pi] = (float)gc10;
+            }
+        }
+    }
+}
+
+size_t herm_smem(int nfft) { return (size_t)4 * nfft * sizeof(cd); }
+
+template <int FPT>
+int herm_launch(W2Params& p, cudaStream_t st) {
+    const size_t smem = herm_smem(p.nfft);
+    if (smem > 48 * 1024)
+        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    SC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, granger_herm_kernel<FPT>, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long long nprob = p.B * p.n_pairs;
+    long long grid = (long long)sc_num_sms() * per_sm;
+    if (grid > nprob) grid = nprob;
+    granger_herm_kernel<FPT><<<(unsigned)grid, kThreads, smem, st>>>(p);
+    SC_LAUNCH_OK();
+    return SC_OK;
+}
+
+}  // namespace
+
+int sc_granger_herm_supported(int nfft) {
+    const int fnn = nfft / 2 + 1;
+    return fnn <= 4 * scw::kThreads && herm_smem(nfft) + 4096 <= (size_t)sc_max_smem_optin();
+}
+
+int sc_granger_herm_launch(scw::W2Params& p, void* stream) {
+    if (sc_fft_make_plan(p.nfft, &p.plan)) {
+        sc_set_error("granger: cannot factorise nfft=%d", p.nfft);
+        return SC_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int fpt = (p.nfft / 2 + 1 + scw::kThreads - 1) / scw::kThreads;
+    switch (fpt) {
+        case 1: return herm_launch<1>(p, st);
+        case 2: return herm_launch<2>(p, st);
+        case 3: return herm_launch<3>(p, st);
+        default: return herm_launch<4>(p, st);
+    }
+}

@@ -14,91 +14,14 @@
 // FFT ping-pong buffers stay in shared memory (or an L2-resident workspace for long FFTs), the
 // 2x2 solves are closed form, convergence is decided on the device, and the Granger log-ratio is
 // written straight into the (B, Fnn, S, S) output.
-#include "fft_device.cuh"
-#include "sc_common.cuh"
+#include "wilson_common.cuh"
+
+int sc_granger_herm_supported(int nfft);
+int sc_granger_herm_launch(scw::W2Params& p, void* stream);
 
 namespace {
 
-typedef cx<double> cd;
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr double kEps64 = 2.220446049250313e-16;
-constexpr double kTikhonov = 1e-12;  // connectivity.py:79
-
-struct W2Params {
-    const void* csm;
-    const float* power;
-    long long B;
-    int F, nfft, herm;
-    long long S;
-    const int* pairs;
-    long long n_pairs;
-    double tol;
-    int max_iter;
-    const cd* tw;
-    void* out;
-    int* iters;
-    int* flags;
-    unsigned char* ws;
-    int use_smem;
-    ScFftPlan plan;
-};
-
-__device__ __forceinline__ cd cdiv1(cd a) {  // 1/a
-    const double d = a.x * a.x + a.y * a.y;
-    return cmake<double>(a.x / d, -a.y / d);
-}
-__device__ __forceinline__ cd cmulc(cd a, cd b) {  // a * conj(b)
-    return cmake<double>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
-}
-__device__ __forceinline__ cd cneg(cd a) { return cmake<double>(-a.x, -a.y); }
-
-template <int NV>
-__device__ __forceinline__ void block_sum(double* v, double* red) {
-#pragma unroll
-    for (int q = 0; q < NV; ++q)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();
-    if (lane == 0)
-#pragma unroll
-        for (int q = 0; q < NV; ++q) red[q * kWarps + warp] = v[q];
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < NV; ++q) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += red[q * kWarps + w];
-        v[q] = s;
-    }
-}
-
-__device__ __forceinline__ double block_max(double v, double* red) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    double m = red[0];
-#pragma unroll
-    for (int w = 1; w < kWarps; ++w) m = fmax(m, red[w]);
-    return m;
-}
-
-__device__ __forceinline__ void decode_pair(long long k, long long S, int& i, int& j) {
-    // k-th pair of combinations(range(S), 2) in lexicographic order
-    const double t = 2.0 * S - 1.0;
-    long long ii = (long long)floor((t - sqrt(t * t - 8.0 * (double)k)) * 0.5);
-    if (ii < 0) ii = 0;
-    if (ii > S - 2) ii = S - 2;
-    while (ii > 0 && ii * (2 * S - ii - 1) / 2 > k) --ii;
-    while ((ii + 1) * (2 * S - ii - 2) / 2 <= k) ++ii;
-    const long long start = ii * (2 * S - ii - 1) / 2;
-    i = (int)ii;
-    j = (int)(ii + 1 + (k - start));
-}
+using namespace scw;
 
 // MODE 0: csm c128 [B][nfft][2][2] -> G c128.  MODE 1: Granger over pairs of a c64 [B][F][S][S] CSM.
 template <int MODE>
@@ -385,5 +308,6 @@ extern "C" int sc_granger_pairwise(const void* csm_c64, const float* power, int6
     p.csm = csm_c64; p.power = power; p.B = B; p.F = F; p.nfft = nfft; p.herm = hermitian_half; p.S = S;
     p.pairs = pairs; p.n_pairs = n_pairs; p.tol = tolerance; p.max_iter = max_iterations;
     p.tw = reinterpret_cast<const cd*>(twiddle_c128); p.out = out_gc; p.iters = out_iters; p.flags = out_flags;
+    if (hermitian_half && sc_granger_herm_supported(nfft)) return sc_granger_herm_launch(p, stream);
     return w2_launch<1>(p, B * n_pairs, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
