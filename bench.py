@@ -242,6 +242,7 @@ def run_gpu(args, wl_name, wl):
         return float(t.item())
 
     # ---- device-resident throughput ------------------------------------------------
+    c = out = None
     for _ in range(args.warmup):
         c, out = step_device()
     del out

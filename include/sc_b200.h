@@ -134,11 +134,16 @@ int sc_wilson2(const void* csm_c128, int64_t B, int nfft, double tolerance, int 
  *  pairs    int32 [n_pairs][2] or NULL for all i<j (then n_pairs is ignored)
  *  out_gc   f32 [B][nfft/2+1][S][S]; entries of processed pairs are overwritten ([i][j] =
  *           influence j -> i); the caller pre-fills the rest (NaN, connectivity.py:2310, 2336-2338)
+ *  tail_extrapolation  0: run the reference iteration verbatim.  1 (hermitian_half only): once the
+ *           update has collapsed onto the reference's geometric lag-0 mode (its plus-operator halves
+ *           the lag-0 coefficient and then zeroes the lower triangle, mpd.py:132-138, so the lag-0
+ *           off-diagonal residual halves per iteration), the remaining iterations are summed in
+ *           closed form up to the iterate the reference stops at; out_iters reports that iterate.
  *  out_iters/out_flags  int32 [n_pairs][B] or NULL */
 int sc_granger_pairwise(const void* csm_c64, const float* power, int64_t B, int F, int nfft, int hermitian_half,
                         int64_t S, const int* pairs, int64_t n_pairs, double tolerance, int max_iterations,
-                        const void* twiddle_c128, float* out_gc, int* out_iters, int* out_flags,
-                        void* workspace, int64_t workspace_bytes, void* stream);
+                        int tail_extrapolation, const void* twiddle_c128, float* out_gc, int* out_iters,
+                        int* out_flags, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t sc_wilson_workspace_bytes(int nfft);
 
 #ifdef __cplusplus

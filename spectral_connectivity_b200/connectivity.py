@@ -209,13 +209,17 @@ class Connectivity:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._reduce_group)
         return t
 
-    def compute(self, measures, pairs=None, tolerance=1e-8, max_iterations=60):
+    def compute(self, measures, pairs=None, tolerance=1e-8, max_iterations=60, tail_extrapolation=True):
         """Compute several measures in ONE streaming pass over window chunks.
 
         ``measures``: iterable of names from ``MEASURES``.  Returns {name: array}.  Per chunk
         the Fourier coefficients, power and cross-spectral matrix are produced once and
-        shared by all requested measures (the reference recomputes them per measure,
-        connectivity.py:146-148 of SURVEY.md section 3.3)."""
+        shared by all requested measures (the reference recomputes them per measure).
+
+        ``tail_extrapolation`` (Granger, real-series path only): sum the geometric tail of the
+        reference's Wilson iteration in closed form instead of iterating through it -- same
+        stopping iterate, same iteration count, results equal to ~1e-7 relative.
+        ``False`` runs every iteration like the reference."""
         lib = _lib.load()
         measures = list(measures)
         for name in measures:
@@ -327,7 +331,8 @@ class Connectivity:
                 with _lib.timed("granger"):
                     rc = lib.sc_granger_pairwise(_lib.ptr(csm), _lib.ptr(power), nb, n_freq, nfft,
                                                  1 if self._hermitian else 0, n_sig, _lib.ptr(pair_t), n_pairs,
-                                                 float(tolerance), int(max_iterations), _lib.ptr(tw128), _lib.ptr(dst),
+                                                 float(tolerance), int(max_iterations), 1 if tail_extrapolation else 0,
+                                                 _lib.ptr(tw128), _lib.ptr(dst),
                                                  _lib.ptr(it_c), _lib.ptr(fl_c), _lib.ptr(gr_ws), ws_bytes, st)
                     _lib.check(rc, "sc_granger_pairwise")
                 it_all[:, b0:b1] = it_c
@@ -455,16 +460,17 @@ class Connectivity:
         """connectivity.py:1129-1159."""
         return self._one("pairwise_phase_consistency")
 
-    def pairwise_spectral_granger_prediction(self, tolerance=1e-8, max_iterations=60):
+    def pairwise_spectral_granger_prediction(self, tolerance=1e-8, max_iterations=60, tail_extrapolation=True):
         """Spectral Granger prediction for every signal pair; [..., i, j] is the influence
         j -> i (connectivity.py:1161-1191)."""
         return self._one("pairwise_spectral_granger_prediction", tolerance=tolerance,
-                         max_iterations=max_iterations)
+                         max_iterations=max_iterations, tail_extrapolation=tail_extrapolation)
 
-    def subset_pairwise_spectral_granger_prediction(self, pairs, tolerance=1e-8, max_iterations=60):
+    def subset_pairwise_spectral_granger_prediction(self, pairs, tolerance=1e-8, max_iterations=60,
+                                                    tail_extrapolation=True):
         """connectivity.py:1193-1213."""
         return self._one("pairwise_spectral_granger_prediction", pairs=pairs, tolerance=tolerance,
-                         max_iterations=max_iterations)
+                         max_iterations=max_iterations, tail_extrapolation=tail_extrapolation)
 
     def conditional_spectral_granger_prediction(self):
         raise NotImplementedError  # connectivity.py:1215-1219

@@ -25,12 +25,16 @@ template <> struct RealOps<float> {
     static __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
 };
 
-// One Wilson iteration on the half spectrum held in registers.  Returns max |dG|^2 of this thread.
+// One Wilson iteration on the half spectrum held in registers.  On return stat[0] = max |dG|^2 of
+// this thread, stat[1] = max |dG - G_prev * eps*U01|^2 (the update with the geometric lag-0
+// off-diagonal mode removed, see granger_herm_kernel), stat[2] = max(|g00|^2, |g10|^2) of G_prev;
+// *eps_smem = lag-0 [0][1] coefficient of the causal factor P.
 template <typename R, int FPT>
-__device__ __forceinline__ R herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[FPT], cx<R> (&g10)[FPT],
-                                            cx<R> (&g11)[FPT], const float (&s00)[FPT], const float (&s11)[FPT],
-                                            const float2 (&s01)[FPT], R sscale, cx<R>* ZA, cx<R>* ZB,
-                                            const ScFftPlan& plan, const cx<R>* tw, int N, int fnn) {
+__device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[FPT], cx<R> (&g10)[FPT],
+                                               cx<R> (&g11)[FPT], const float (&s00)[FPT], const float (&s11)[FPT],
+                                               const float2 (&s01)[FPT], R sscale, cx<R>* ZA, cx<R>* ZB,
+                                               const ScFftPlan& plan, const cx<R>* tw, int N, int fnn,
+                                               R* eps_smem, R (&stat)[3]) {
     // ---- linear predictor (mpd.py:218-224), Hermitian: b00, b11 real, b10 = conj(b01) ----
 #pragma unroll
     for (int q = 0; q < FPT; ++q) {
@@ -78,6 +82,7 @@ __device__ __forceinline__ R herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[FPT]
             const R c10 = k == 0 ? (R)0 : c[N + (N - k)].x;  // c10[k] = c01[-k]; zeroed at lag 0
             y1 = cmake<R>(z1.x * w, c01 * w);       // p00 + i p01
             y2 = cmake<R>(c10 * w, z1.y * w);       // p10 + i p11
+            if (k == 0) *eps_smem = c01 * w;
         }
         o[k] = y1;
         o[N + k] = y2;
@@ -85,7 +90,8 @@ __device__ __forceinline__ R herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[FPT]
     __syncthreads();
     const cx<R>* Q = sc_cta_fft<R, true>(o, c, 2, N, plan, tw, false);
     // ---- G <- G P (mpd.py:305-307) ----
-    R err2 = (R)0;
+    R err2 = (R)0, rest2 = (R)0, gmax2 = (R)0;
+    const R eps = *eps_smem;
 #pragma unroll
     for (int q = 0; q < FPT; ++q) {
         const int f = threadIdx.x + q * kThreads;
@@ -102,14 +108,18 @@ __device__ __forceinline__ R herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[FPT]
             const cx<R> n10 = cadd(cmul(g10[q], p00), cmul(g11[q], p10));
             const cx<R> n11 = cadd(cmul(g10[q], p01), cmul(g11[q], p11));
             cx<R> dd;
-            dd = csub(n00, g00[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
+            R e;
+            dd = csub(n00, g00[q]); e = dd.x * dd.x + dd.y * dd.y; err2 = fmax(err2, e); rest2 = fmax(rest2, e);
+            dd = csub(n10, g10[q]); e = dd.x * dd.x + dd.y * dd.y; err2 = fmax(err2, e); rest2 = fmax(rest2, e);
             dd = csub(n01, g01[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
-            dd = csub(n10, g10[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
+            dd.x -= eps * g00[q].x; dd.y -= eps * g00[q].y; rest2 = fmax(rest2, dd.x * dd.x + dd.y * dd.y);
             dd = csub(n11, g11[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
+            dd.x -= eps * g10[q].x; dd.y -= eps * g10[q].y; rest2 = fmax(rest2, dd.x * dd.x + dd.y * dd.y);
+            gmax2 = fmax(gmax2, fmax(g00[q].x * g00[q].x + g00[q].y * g00[q].y, g10[q].x * g10[q].x + g10[q].y * g10[q].y));
             g00[q] = n00; g01[q] = n01; g10[q] = n10; g11[q] = n11;
         }
     }
-    return err2;
+    stat[0] = err2; stat[1] = rest2; stat[2] = gmax2;
 }
 
 template <int FPT>
@@ -118,8 +128,11 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
     __shared__ double red[4 * kWarps];
     const int N = p.nfft;
     const int fnn = N / 2 + 1;
+    __shared__ double eps_sh;
     cd* ZA = reinterpret_cast<cd*>(smem_raw);
     cd* ZB = ZA + 2 * (size_t)N;
+    cd* tws = ZB + 2 * (size_t)N;
+    for (int q = threadIdx.x; q < N; q += kThreads) tws[q] = p.tw[q];
     const long long npairs = p.n_pairs;
     const long long nprob = p.B * npairs;
     const float fnan = __int_as_float(0x7fc00000);
@@ -167,11 +180,41 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
         if (!flag) {
             bool converged = false;
             for (int it = 0; it < p.max_iter && !converged; ++it) {
-                const double e2 = herm_iteration<double, FPT>(g00, g01, g10, g11, s00, s11, s01, 1.0, ZA, ZB, p.plan,
-                                                              p.tw, N, fnn);
-                const double err = sqrt(block_max(e2, red));  // also fences ZA/ZB reuse
+                double st[3];
+                herm_iteration<double, FPT>(g00, g01, g10, g11, s00, s11, s01, 1.0, ZA, ZB, p.plan, tws, N, fnn,
+                                            &eps_sh, st);
+                block_max3(st, red);  // also fences ZA/ZB reuse
+                const double err = sqrt(st[0]);
                 it_done = it + 1;
                 converged = err < p.tol;
+                if (!converged && p.tail && p.tol > 0.0) {
+                    // Tail extrapolation.  The reference halves every lag-0 entry of the causal factor and
+                    // THEN zeroes its lower triangle (mpd.py:132-138), so the lag-0 off-diagonal residual is
+                    // only half-corrected per iteration: once every other mode has converged, each further
+                    // iteration is G <- G (I + eps U01) with eps halving (U01 = [[0,1],[0,0]]).  When the
+                    // update is that mode alone (rest < tol) and its second-order effect is below tol, the
+                    // remaining iterations of the reference are summed in closed form, stopping at the same
+                    // iterate K the reference would stop at (first with max|dG| < tol).
+                    const double eps = eps_sh;
+                    const double e_abs = fabs(eps), mnorm = sqrt(st[2]);
+                    if (sqrt(st[1]) < p.tol && e_abs * e_abs * mnorm < p.tol) {
+                        int m = 1;
+                        double d = 0.5 * e_abs * mnorm;
+                        while (d >= p.tol && it_done + m < p.max_iter) {
+                            d *= 0.5;
+                            ++m;
+                        }
+                        const double ssum = eps * (1.0 - ldexp(1.0, -m));  // eps * sum_{q=1..m} 2^-q
+#pragma unroll
+                        for (int q = 0; q < FPT; ++q) {
+                            g01[q].x += ssum * g00[q].x; g01[q].y += ssum * g00[q].y;
+                            g11[q].x += ssum * g10[q].x; g11[q].y += ssum * g10[q].y;
+                        }
+                        it_done += m;
+                        converged = d < p.tol;
+                        break;
+                    }
+                }
             }
             if (!converged) flag |= SC_FLAG_NOT_CONVERGED;
         }
@@ -231,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
     }
 }
 
-size_t herm_smem(int nfft) { return (size_t)4 * nfft * sizeof(cd); }
+size_t herm_smem(int nfft) { return (size_t)5 * nfft * sizeof(cd); }  // ZA, ZB (2 sequences each), twiddles
 
 template <int FPT>
 int herm_launch(W2Params& p, cudaStream_t st) {

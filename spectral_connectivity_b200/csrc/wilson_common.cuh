@@ -27,6 +27,7 @@ struct W2Params {
     int* flags;
     unsigned char* ws;
     int use_smem;
+    int tail;  // 1: sum the geometric tail of the reference iteration in closed form (Hermitian kernel)
     ScFftPlan plan;
 };
 
@@ -57,6 +58,26 @@ __device__ __forceinline__ void block_sum(double* v, double* red) {
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) s += red[q * kWarps + w];
         v[q] = s;
+    }
+}
+
+__device__ __forceinline__ void block_max3(double (&v)[3], double* red) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] = fmax(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) red[q * kWarps + warp] = v[q];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        double m = red[q * kWarps];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) m = fmax(m, red[q * kWarps + w]);
+        v[q] = m;
     }
 }
 
