@@ -204,10 +204,8 @@ SC_HD void sc_dft(cx<R>* v, bool inv, const cx<R>* tw, int n) {
 // sub-length is Ls: reads src[j + t*n/RADIX], writes dst[(j-k)*RADIX + k + q*Ls], k = j % Ls.
 // tw[q] = exp(-2 pi i q/n), q in [0, n).
 template <typename R, int RADIX>
-SC_HD void sc_fft_item(const cx<R>* src, cx<R>* dst, int j, int n, int Ls, const cx<R>* tw, bool inv) {
-    const int m = n / RADIX;
-    const int k = j % Ls;
-    const int tws = m / Ls;  // n / (Ls*RADIX)
+SC_HD void sc_fft_item_k(const cx<R>* src, cx<R>* dst, int j, int k, int n, int m, int Ls, int tws, const cx<R>* tw,
+                         bool inv) {
     cx<R> v[RADIX];
 #pragma unroll
     for (int t = 0; t < RADIX; ++t) v[t] = src[j + t * m];
@@ -223,6 +221,12 @@ SC_HD void sc_fft_item(const cx<R>* src, cx<R>* dst, int j, int n, int Ls, const
     const int ob = (j - k) * RADIX + k;
 #pragma unroll
     for (int q = 0; q < RADIX; ++q) dst[ob + q * Ls] = v[q];
+}
+
+template <typename R, int RADIX>
+SC_HD void sc_fft_item(const cx<R>* src, cx<R>* dst, int j, int n, int Ls, const cx<R>* tw, bool inv) {
+    const int m = n / RADIX;
+    sc_fft_item_k<R, RADIX>(src, dst, j, j % Ls, n, m, Ls, m / Ls, tw, inv);
 }
 
 // Runtime-radix fallback (large prime factors): item = (j, q) pair, 0 <= item < n.
@@ -244,16 +248,137 @@ SC_HD void sc_fft_item_generic(const cx<R>* src, cx<R>* dst, int item, int radix
     dst[(j - k) * radix + k + q * Ls] = acc;
 }
 
+// ---------------------------------------------------------------------------
+// Compile-time plans: every stride, sub-length and twiddle offset is a constant, so loads and
+// stores become [reg + immediate] and the modulo by Ls a multiply-shift.  Twiddles come from
+// per-stage tables T_s[(t-1)*Ls + k] = W_N^(t*k*N/(Ls*r)) laid out with k fastest, which
+// consecutive butterflies read without shared-memory bank conflicts (the flat table read
+// tw[t*k*tws] is a strided gather).  Only the register radices 2,3,4,5,8,10 are allowed.
+// ---------------------------------------------------------------------------
+template <int N, int... RS> struct ScStaticPlan {
+    static constexpr int n = N;
+};
+
+template <int LS, int R0, int... REST> struct ScTwCount {
+    static constexpr int value = (LS > 1 ? (R0 - 1) * LS : 0) + ScTwCount<LS * R0, REST...>::value;
+};
+template <int LS, int R0> struct ScTwCount<LS, R0> {
+    static constexpr int value = (LS > 1 ? (R0 - 1) * LS : 0);
+};
+
+// number of stage-twiddle entries of a plan
+template <typename PLAN> struct ScStaticTw;
+template <int N, int... RS> struct ScStaticTw<ScStaticPlan<N, RS...>> {
+    static constexpr int count = ScTwCount<1, RS...>::value;
+};
+
+template <typename R, int N, int LS, int RADIX>
+SC_HD void sc_static_item(const cx<R>* src, cx<R>* dst, int j, const cx<R>* tws, bool inv) {
+    constexpr int M = N / RADIX;
+    const int k = LS == 1 ? 0 : (LS == M ? j : j % LS);
+    cx<R> v[RADIX];
+#pragma unroll
+    for (int t = 0; t < RADIX; ++t) v[t] = src[j + t * M];
+    if (LS > 1) {
+#pragma unroll
+        for (int t = 1; t < RADIX; ++t) {
+            cx<R> w = tws[(t - 1) * LS + k];
+            if (inv) w.y = -w.y;
+            v[t] = cmul(v[t], w);
+        }
+    }
+    sc_dft<R, RADIX>(v, inv, (const cx<R>*)0, N);
+    const int ob = (j - k) * RADIX + k;
+#pragma unroll
+    for (int q = 0; q < RADIX; ++q) dst[ob + q * LS] = v[q];
+}
+
+// fill the stage tables of one stage from the flat table tw[q] = exp(-2 pi i q/N)
+template <typename R, int N, int LS, int RADIX>
+SC_HD void sc_static_fill_stage(cx<R>* tws, const cx<R>* tw, int tid, int nthreads) {
+    if (LS > 1) {
+        constexpr int TWS = N / (LS * RADIX);
+        for (int e = tid; e < (RADIX - 1) * LS; e += nthreads) {
+            const int t = e / LS + 1, k = e % LS;
+            tws[e] = tw[t * k * TWS];
+        }
+    }
+}
+
+template <typename R, int N, int LS, int R0, int... REST> struct ScStaticStages {
+    static constexpr int TWN = (LS > 1 ? (R0 - 1) * LS : 0);
+    // SYNC is called after every stage (device: __syncthreads, host tests: no-op)
+    template <int NB, typename SYNC>
+    static SC_HD cx<R>* run(cx<R>* src, cx<R>* dst, const cx<R>* tws, bool inv, int tid, int nthreads, SYNC sync) {
+        constexpr int M = N / R0;
+        for (int idx = tid; idx < NB * M; idx += nthreads) {
+            const int bb = idx / M, j = idx % M;
+            sc_static_item<R, N, LS, R0>(src + bb * N, dst + bb * N, j, tws, inv);
+        }
+        sync();
+        return ScStaticStages<R, N, LS * R0, REST...>::template run<NB>(dst, src, tws + TWN, inv, tid, nthreads, sync);
+    }
+    static SC_HD void fill(cx<R>* tws, const cx<R>* tw, int tid, int nthreads) {
+        sc_static_fill_stage<R, N, LS, R0>(tws, tw, tid, nthreads);
+        ScStaticStages<R, N, LS * R0, REST...>::fill(tws + TWN, tw, tid, nthreads);
+    }
+};
+template <typename R, int N, int LS, int R0> struct ScStaticStages<R, N, LS, R0> {
+    static_assert(LS * R0 == N, "radices must multiply to N");
+    template <int NB, typename SYNC>
+    static SC_HD cx<R>* run(cx<R>* src, cx<R>* dst, const cx<R>* tws, bool inv, int tid, int nthreads, SYNC sync) {
+        constexpr int M = N / R0;
+        for (int idx = tid; idx < NB * M; idx += nthreads) {
+            const int bb = idx / M, j = idx % M;
+            sc_static_item<R, N, LS, R0>(src + bb * N, dst + bb * N, j, tws, inv);
+        }
+        sync();
+        return dst;
+    }
+    static SC_HD void fill(cx<R>* tws, const cx<R>* tw, int tid, int nthreads) {
+        sc_static_fill_stage<R, N, LS, R0>(tws, tw, tid, nthreads);
+    }
+};
+
+template <typename R, typename PLAN> struct ScStaticFft;
+template <typename R, int N, int... RS> struct ScStaticFft<R, ScStaticPlan<N, RS...>> {
+    static constexpr int n = N;
+    static constexpr int tw_count = ScTwCount<1, RS...>::value;
+    // NB transforms of length N at a + b*N; returns the buffer holding the (unnormalised) result
+    template <int NB, typename SYNC>
+    static SC_HD cx<R>* run(cx<R>* a, cx<R>* b, const cx<R>* tws, bool inv, int tid, int nthreads, SYNC sync) {
+        return ScStaticStages<R, N, 1, RS...>::template run<NB>(a, b, tws, inv, tid, nthreads, sync);
+    }
+    static SC_HD void fill(cx<R>* tws, const cx<R>* tw, int tid, int nthreads) {
+        ScStaticStages<R, N, 1, RS...>::fill(tws, tw, tid, nthreads);
+    }
+};
+
+typedef ScStaticPlan<1000, 10, 10, 10> ScPlan1000;
+typedef ScStaticPlan<120, 10, 4, 3> ScPlan120;
+
 #if defined(__CUDACC__)
 template <typename R, int RADIX>
 __device__ __forceinline__ void sc_cta_fft_pass(const cx<R>* src, cx<R>* dst, int nbatch, int bstride, int n,
                                                 int Ls, const cx<R>* tw, bool inv) {
+    // Integer divisions are hoisted out of the per-butterfly path: the first stage has k = 0, the
+    // last stage has k = j, and the batch index advances by carry instead of idx / m.
     const int m = n / RADIX;
+    const int tws = m / Ls;
     const int total = nbatch * m;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int bb = idx / m;
-        const int j = idx - bb * m;
-        sc_fft_item<R, RADIX>(src + (size_t)bb * bstride, dst + (size_t)bb * bstride, j, n, Ls, tw, inv);
+    const int step = blockDim.x;
+    const int step_b = step / m, step_j = step - step_b * m;
+    int bb = threadIdx.x / m;
+    int j = threadIdx.x - bb * m;
+    for (int idx = threadIdx.x; idx < total; idx += step) {
+        const int k = Ls == 1 ? 0 : (Ls == m ? j : j % Ls);
+        sc_fft_item_k<R, RADIX>(src + (size_t)bb * bstride, dst + (size_t)bb * bstride, j, k, n, m, Ls, tws, tw, inv);
+        j += step_j;
+        bb += step_b;
+        if (j >= m) {
+            j -= m;
+            ++bb;
+        }
     }
 }
 

@@ -17,6 +17,35 @@ namespace {
 
 using namespace scw;
 
+struct CtaSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+// FFT policies: runtime plan (any length) or a compile-time plan (fft_device.cuh).
+struct DynFft {
+    static __host__ __device__ int tw_entries(int n) { return n; }
+    template <typename R>
+    static __device__ __forceinline__ void fill(cx<R>* tws, const cx<R>* tw, int n) {
+        for (int q = threadIdx.x; q < n; q += kThreads) tws[q] = tw[q];
+    }
+    template <typename R>
+    static __device__ __forceinline__ cx<R>* run2(cx<R>* a, cx<R>* b, const ScFftPlan& plan, const cx<R>* tws,
+                                                  bool inv) {
+        return sc_cta_fft<R, true>(a, b, 2, plan.n, plan, tws, inv);
+    }
+};
+template <typename PLAN> struct StatFft {
+    static __host__ __device__ int tw_entries(int) { return ScStaticTw<PLAN>::count; }
+    template <typename R>
+    static __device__ __forceinline__ void fill(cx<R>* tws, const cx<R>* tw, int) {
+        ScStaticFft<R, PLAN>::fill(tws, tw, threadIdx.x, kThreads);
+    }
+    template <typename R>
+    static __device__ __forceinline__ cx<R>* run2(cx<R>* a, cx<R>* b, const ScFftPlan&, const cx<R>* tws, bool inv) {
+        return ScStaticFft<R, PLAN>::template run<2>(a, b, tws, inv, threadIdx.x, kThreads, CtaSync());
+    }
+};
+
 template <typename R> struct RealOps;
 template <> struct RealOps<double> {
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
@@ -29,7 +58,7 @@ template <> struct RealOps<float> {
 // this thread, stat[1] = max |dG - G_prev * eps*U01|^2 (the update with the geometric lag-0
 // off-diagonal mode removed, see granger_herm_kernel), stat[2] = max(|g00|^2, |g10|^2) of G_prev;
 // *eps_smem = lag-0 [0][1] coefficient of the causal factor P.
-template <typename R, int FPT>
+template <typename R, int FPT, typename FFT>
 __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[FPT], cx<R> (&g10)[FPT],
                                                cx<R> (&g11)[FPT], const float (&s00)[FPT], const float (&s11)[FPT],
                                                const float2 (&s01)[FPT], R sscale, cx<R>* ZA, cx<R>* ZB,
@@ -69,7 +98,7 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
     }
     __syncthreads();
     // ---- plus operator (mpd.py:129-142) on the real sequences, packed for the forward FFTs ----
-    cx<R>* c = sc_cta_fft<R, true>(ZA, ZB, 2, N, plan, tw, true);
+    cx<R>* c = FFT::template run2<R>(ZA, ZB, plan, tw, true);
     cx<R>* o = (c == ZA) ? ZB : ZA;
     const R inv_n = (R)1 / (R)N;
     const int kcut = (N + 1) / 2;
@@ -88,7 +117,7 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
         o[N + k] = y2;
     }
     __syncthreads();
-    const cx<R>* Q = sc_cta_fft<R, true>(o, c, 2, N, plan, tw, false);
+    const cx<R>* Q = FFT::template run2<R>(o, c, plan, tw, false);
     // ---- G <- G P (mpd.py:305-307) ----
     R err2 = (R)0, rest2 = (R)0, gmax2 = (R)0;
     const R eps = *eps_smem;
@@ -122,7 +151,7 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
     stat[0] = err2; stat[1] = rest2; stat[2] = gmax2;
 }
 
-template <int FPT>
+template <int FPT, typename FFT>
 __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[4 * kWarps];
@@ -132,7 +161,8 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
     cd* ZA = reinterpret_cast<cd*>(smem_raw);
     cd* ZB = ZA + 2 * (size_t)N;
     cd* tws = ZB + 2 * (size_t)N;
-    for (int q = threadIdx.x; q < N; q += kThreads) tws[q] = p.tw[q];
+    FFT::template fill<double>(tws, p.tw, N);
+    __syncthreads();
     const long long npairs = p.n_pairs;
     const long long nprob = p.B * npairs;
     const float fnan = __int_as_float(0x7fc00000);
@@ -181,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
             bool converged = false;
             for (int it = 0; it < p.max_iter && !converged; ++it) {
                 double st[3];
-                herm_iteration<double, FPT>(g00, g01, g10, g11, s00, s11, s01, 1.0, ZA, ZB, p.plan, tws, N, fnn,
+                herm_iteration<double, FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, 1.0, ZA, ZB, p.plan, tws, N, fnn,
                                             &eps_sh, st);
                 block_max3(st, red);  // also fences ZA/ZB reuse
                 const double err = sqrt(st[0]);
@@ -276,18 +306,19 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
 
 size_t herm_smem(int nfft) { return (size_t)5 * nfft * sizeof(cd); }  // ZA, ZB (2 sequences each), twiddles
 
-template <int FPT>
+template <int FPT, typename FFT>
 int herm_launch(W2Params& p, cudaStream_t st) {
-    const size_t smem = herm_smem(p.nfft);
+    const size_t smem = (size_t)(4 * p.nfft + FFT::tw_entries(p.nfft)) * sizeof(cd);
     if (smem > 48 * 1024)
-        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
     int per_sm = 1;
-    SC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, granger_herm_kernel<FPT>, kThreads, smem));
+    SC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, granger_herm_kernel<FPT, FFT>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
     const long long nprob = p.B * p.n_pairs;
     long long grid = (long long)sc_num_sms() * per_sm;
     if (grid > nprob) grid = nprob;
-    granger_herm_kernel<FPT><<<(unsigned)grid, kThreads, smem, st>>>(p);
+    granger_herm_kernel<FPT, FFT><<<(unsigned)grid, kThreads, smem, st>>>(p);
     SC_LAUNCH_OK();
     return SC_OK;
 }
@@ -305,11 +336,13 @@ int sc_granger_herm_launch(scw::W2Params& p, void* stream) {
         return SC_ERR_UNSUPPORTED;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (p.nfft == 1000) return herm_launch<2, StatFft<ScPlan1000>>(p, st);
+    if (p.nfft == 120) return herm_launch<1, StatFft<ScPlan120>>(p, st);
     const int fpt = (p.nfft / 2 + 1 + scw::kThreads - 1) / scw::kThreads;
     switch (fpt) {
-        case 1: return herm_launch<1>(p, st);
-        case 2: return herm_launch<2>(p, st);
-        case 3: return herm_launch<3>(p, st);
-        default: return herm_launch<4>(p, st);
+        case 1: return herm_launch<1, DynFft>(p, st);
+        case 2: return herm_launch<2, DynFft>(p, st);
+        case 3: return herm_launch<3, DynFft>(p, st);
+        default: return herm_launch<4, DynFft>(p, st);
     }
 }

@@ -56,6 +56,32 @@ extern "C" int fft_host_f64(double* data, int n, int inverse, int force_generic)
 extern "C" int fft_host_f32(float* data, int n, int inverse, int force_generic) {
     return run<float>(data, n, inverse, force_generic);
 }
+template <typename PLAN>
+static int run_static(double* data, int inverse) {
+    typedef ScStaticFft<double, PLAN> F;
+    const int n = F::n;
+    std::vector<cx<double>> a(n), b(n), tw(n), tws(F::tw_count + 1);
+    for (int i = 0; i < n; ++i) {
+        a[i].x = data[2 * i];
+        a[i].y = data[2 * i + 1];
+        tw[i].x = cos(-2.0 * M_PI * i / n);
+        tw[i].y = sin(-2.0 * M_PI * i / n);
+    }
+    F::fill(tws.data(), tw.data(), 0, 1);
+    cx<double>* res = F::template run<1>(a.data(), b.data(), tws.data(), inverse != 0, 0, 1, [] {});
+    for (int i = 0; i < n; ++i) {
+        data[2 * i] = res[i].x;
+        data[2 * i + 1] = res[i].y;
+    }
+    return F::tw_count;
+}
+
+extern "C" int fft_static_f64(double* data, int n, int inverse) {
+    if (n == 1000) return run_static<ScPlan1000>(data, inverse);
+    if (n == 120) return run_static<ScPlan120>(data, inverse);
+    return -1;
+}
+
 extern "C" int fft_plan(int n, int* radices) {
     ScFftPlan plan;
     if (sc_fft_make_plan(n, &plan)) return -1;

