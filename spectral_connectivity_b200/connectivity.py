@@ -278,6 +278,24 @@ class Connectivity:
             it_all = torch.zeros((n_pairs, n_batch), dtype=torch.int32, device=dev)
             fl_all = torch.zeros((n_pairs, n_batch), dtype=torch.int32, device=dev)
 
+        # output="numpy": stream each finished chunk to pinned host memory on a side stream while the
+        # next chunk computes
+        host, copy_stream = {}, None
+        if self._output == "numpy":
+            copy_stream = torch.cuda.Stream(device=dev)
+            for name, t in out.items():
+                shp = (t.shape[0], fnn) + tuple(t.shape[2:])
+                host[name] = torch.empty(shp, dtype=t.dtype, pin_memory=True)
+
+        def offload(name, b0, b1):
+            if copy_stream is None:
+                return
+            ev = torch.cuda.Event()
+            ev.record()
+            copy_stream.wait_event(ev)
+            with torch.cuda.stream(copy_stream):
+                host[name][b0:b1].copy_(out[name][b0:b1, :fnn], non_blocking=True)
+
         st = _lib.stream_ptr()
         for b0, b1, xp, nr in self._chunks(n_freq):
             nb = b1 - b0
@@ -289,6 +307,7 @@ class Connectivity:
                 self._allreduce(power)
                 if "power" in out:
                     out["power"][b0:b1] = power
+                    offload("power", b0, b1)
             if "csm" in needs:
                 csm = torch.empty((nb, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
                 with _lib.timed("csm"):
@@ -297,6 +316,7 @@ class Connectivity:
                 self._allreduce(csm)
                 if "expectation_cross_spectral_matrix" in out:
                     out["expectation_cross_spectral_matrix"][b0:b1] = csm
+                    offload("expectation_cross_spectral_matrix", b0, b1)
             plv = pli = None
             if "plv" in needs:
                 plv = torch.empty((nb, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
@@ -306,6 +326,7 @@ class Connectivity:
                 self._allreduce(plv)
                 if "_phase_locking_value" in out:
                     out["_phase_locking_value"][b0:b1] = plv
+                    offload("_phase_locking_value", b0, b1)
             if "pli" in needs:
                 pli = torch.empty((4, nb, n_freq, n_sig, n_sig), dtype=torch.float32, device=dev)
                 with _lib.timed("pli"):
@@ -324,6 +345,7 @@ class Connectivity:
                                                         _lib.ptr(power) if src_kind == "csm" else None, nb, n_freq,
                                                         n_sig, float(self.n_observations), _lib.ptr(dst), st),
                                f"sc_pairwise_epilogue[{name}]")
+                offload(name, b0, b1)
             if want_granger:
                 it_c = torch.zeros((n_pairs, nb), dtype=torch.int32, device=dev)
                 fl_c = torch.zeros((n_pairs, nb), dtype=torch.int32, device=dev)
@@ -337,6 +359,7 @@ class Connectivity:
                     _lib.check(rc, "sc_granger_pairwise")
                 it_all[:, b0:b1] = it_c
                 fl_all[:, b0:b1] = fl_c
+                offload("pairwise_spectral_granger_prediction", b0, b1)
 
         if want_granger:
             self.last_granger_iterations = it_all
@@ -350,11 +373,16 @@ class Connectivity:
                                "(pair, window) problems; their Granger values are NaN.")
 
         result = {}
+        if copy_stream is not None:
+            copy_stream.synchronize()
+            for name, t in host.items():
+                result[name] = t.reshape(kept + tuple(t.shape[1:])).numpy()
+            return result
         for name, t in out.items():
             if t.shape[1] != fnn:
                 t = t[:, :fnn]
             tail = tuple(t.shape[1:])
-            result[name] = self._finish(t.reshape(kept + tail))
+            result[name] = t.reshape(kept + tail)
         return result
 
     def _one(self, name, **kw):
