@@ -55,15 +55,16 @@ template <> struct RealOps<float> {
 };
 
 // One Wilson iteration on the half spectrum held in registers.  On return stat[0] = max |dG|^2 of
-// this thread, stat[1] = max |dG - G_prev * eps*U01|^2 (the update with the geometric lag-0
-// off-diagonal mode removed, see granger_herm_kernel), stat[2] = max(|g00|^2, |g10|^2) of G_prev;
-// *eps_smem = lag-0 [0][1] coefficient of the causal factor P.
+// this thread, stat[1] = max |dG - G_prev (P0 - I)|^2 where P0 is the lag-0 (constant) part of the
+// causal factor (the update with the constant-matrix mode removed, see granger_herm_kernel),
+// stat[2..5] = max over this thread's bins of |g00|^2, |g10|^2, |g01|^2, |g11|^2 of G_prev;
+// lag0[0..2] = lag-0 residual e00, e01, e11 of G^-1 S G^-H - I (real for real time series).
 template <typename R, int FPT, typename FFT>
 __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[FPT], cx<R> (&g10)[FPT],
                                                cx<R> (&g11)[FPT], const float (&s00)[FPT], const float (&s11)[FPT],
                                                const float2 (&s01)[FPT], R sscale, cx<R>* ZA, cx<R>* ZB,
                                                const ScFftPlan& plan, const cx<R>* tw, int N, int fnn,
-                                               R* eps_smem, R (&stat)[3]) {
+                                               R* lag0, R (&stat)[6]) {
     // ---- linear predictor (mpd.py:218-224), Hermitian: b00, b11 real, b10 = conj(b01) ----
 #pragma unroll
     for (int q = 0; q < FPT; ++q) {
@@ -111,7 +112,11 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
             const R c10 = k == 0 ? (R)0 : c[N + (N - k)].x;  // c10[k] = c01[-k]; zeroed at lag 0
             y1 = cmake<R>(z1.x * w, c01 * w);       // p00 + i p01
             y2 = cmake<R>(c10 * w, z1.y * w);       // p10 + i p11
-            if (k == 0) *eps_smem = c01 * w;
+            if (k == 0) {
+                lag0[0] = z1.x * inv_n - (R)2;
+                lag0[1] = c01 * inv_n;
+                lag0[2] = z1.y * inv_n - (R)2;
+            }
         }
         o[k] = y1;
         o[N + k] = y2;
@@ -119,8 +124,8 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
     __syncthreads();
     const cx<R>* Q = FFT::template run2<R>(o, c, plan, tw, false);
     // ---- G <- G P (mpd.py:305-307) ----
-    R err2 = (R)0, rest2 = (R)0, gmax2 = (R)0;
-    const R eps = *eps_smem;
+    R err2 = (R)0, rest2 = (R)0, c00 = (R)0, c10 = (R)0, c01m = (R)0, c11m = (R)0;
+    const R h00 = (R)0.5 * lag0[0], h01 = (R)0.5 * lag0[1], h11 = (R)0.5 * lag0[2];  // P0 - I
 #pragma unroll
     for (int q = 0; q < FPT; ++q) {
         const int f = threadIdx.x + q * kThreads;
@@ -137,27 +142,33 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
             const cx<R> n10 = cadd(cmul(g10[q], p00), cmul(g11[q], p10));
             const cx<R> n11 = cadd(cmul(g10[q], p01), cmul(g11[q], p11));
             cx<R> dd;
-            R e;
-            dd = csub(n00, g00[q]); e = dd.x * dd.x + dd.y * dd.y; err2 = fmax(err2, e); rest2 = fmax(rest2, e);
-            dd = csub(n10, g10[q]); e = dd.x * dd.x + dd.y * dd.y; err2 = fmax(err2, e); rest2 = fmax(rest2, e);
+            dd = csub(n00, g00[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
+            dd.x -= h00 * g00[q].x; dd.y -= h00 * g00[q].y; rest2 = fmax(rest2, dd.x * dd.x + dd.y * dd.y);
+            dd = csub(n10, g10[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
+            dd.x -= h00 * g10[q].x; dd.y -= h00 * g10[q].y; rest2 = fmax(rest2, dd.x * dd.x + dd.y * dd.y);
             dd = csub(n01, g01[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
-            dd.x -= eps * g00[q].x; dd.y -= eps * g00[q].y; rest2 = fmax(rest2, dd.x * dd.x + dd.y * dd.y);
+            dd.x -= h01 * g00[q].x + h11 * g01[q].x; dd.y -= h01 * g00[q].y + h11 * g01[q].y;
+            rest2 = fmax(rest2, dd.x * dd.x + dd.y * dd.y);
             dd = csub(n11, g11[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
-            dd.x -= eps * g10[q].x; dd.y -= eps * g10[q].y; rest2 = fmax(rest2, dd.x * dd.x + dd.y * dd.y);
-            gmax2 = fmax(gmax2, fmax(g00[q].x * g00[q].x + g00[q].y * g00[q].y, g10[q].x * g10[q].x + g10[q].y * g10[q].y));
+            dd.x -= h01 * g10[q].x + h11 * g11[q].x; dd.y -= h01 * g10[q].y + h11 * g11[q].y;
+            rest2 = fmax(rest2, dd.x * dd.x + dd.y * dd.y);
+            c00 = fmax(c00, g00[q].x * g00[q].x + g00[q].y * g00[q].y);
+            c10 = fmax(c10, g10[q].x * g10[q].x + g10[q].y * g10[q].y);
+            c01m = fmax(c01m, g01[q].x * g01[q].x + g01[q].y * g01[q].y);
+            c11m = fmax(c11m, g11[q].x * g11[q].x + g11[q].y * g11[q].y);
             g00[q] = n00; g01[q] = n01; g10[q] = n10; g11[q] = n11;
         }
     }
-    stat[0] = err2; stat[1] = rest2; stat[2] = gmax2;
+    stat[0] = err2; stat[1] = rest2; stat[2] = c00; stat[3] = c10; stat[4] = c01m; stat[5] = c11m;
 }
 
 template <int FPT, typename FFT>
 __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[4 * kWarps];
+    __shared__ double red[6 * kWarps];
     const int N = p.nfft;
     const int fnn = N / 2 + 1;
-    __shared__ double eps_sh;
+    __shared__ double lag0_sh[3];
     cd* ZA = reinterpret_cast<cd*>(smem_raw);
     cd* ZB = ZA + 2 * (size_t)N;
     cd* tws = ZB + 2 * (size_t)N;
@@ -210,40 +221,52 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
         if (!flag) {
             bool converged = false;
             for (int it = 0; it < p.max_iter && !converged; ++it) {
-                double st[3];
+                double st[6];
                 herm_iteration<double, FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, 1.0, ZA, ZB, p.plan, tws, N, fnn,
-                                            &eps_sh, st);
-                block_max3(st, red);  // also fences ZA/ZB reuse
+                                                 lag0_sh, st);
+                block_maxn<6>(st, red);  // also fences ZA/ZB reuse
                 const double err = sqrt(st[0]);
                 it_done = it + 1;
                 converged = err < p.tol;
-                if (!converged && p.tail && p.tol > 0.0) {
-                    // Tail extrapolation.  The reference halves every lag-0 entry of the causal factor and
-                    // THEN zeroes its lower triangle (mpd.py:132-138), so the lag-0 off-diagonal residual is
-                    // only half-corrected per iteration: once every other mode has converged, each further
-                    // iteration is G <- G (I + eps U01) with eps halving (U01 = [[0,1],[0,0]]).  When the
-                    // update is that mode alone (rest < tol) and its second-order effect is below tol, the
-                    // remaining iterations of the reference are summed in closed form, stopping at the same
-                    // iterate K the reference would stop at (first with max|dG| < tol).
-                    const double eps = eps_sh;
-                    const double e_abs = fabs(eps), mnorm = sqrt(st[2]);
-                    if (sqrt(st[1]) < p.tol && e_abs * e_abs * mnorm < p.tol) {
-                        int m = 1;
-                        double d = 0.5 * e_abs * mnorm;
-                        while (d >= p.tol && it_done + m < p.max_iter) {
-                            d *= 0.5;
-                            ++m;
+                if (!converged && p.tail && sqrt(st[1]) < p.tol) {
+                    // Tail in closed form.  The reference halves every lag-0 coefficient of the causal factor
+                    // and THEN zeroes its lower triangle (mpd.py:132-138), so the lag-0 off-diagonal residual
+                    // is only half-corrected per iteration: once every other mode has converged (the update
+                    // minus its constant-matrix part is below tol), all further iterations multiply G by
+                    // constant upper-triangular 2x2 matrices P_j = I + upper_half(E_j), with
+                    // E_j = C_j^-1 (I + e0) C_j^-T - I and C_{j+1} = C_j P_j.  That 2x2 recursion is run here
+                    // exactly, up to the iterate at which the reference stops (first max|dG| < tol).
+                    const double e00 = lag0_sh[0], e01 = lag0_sh[1], e11 = lag0_sh[2];
+                    const double m00 = 1.0 + e00, m01 = e01, m11 = 1.0 + e11;  // I + e0 (symmetric)
+                    double ca = 1.0 + 0.5 * e00, cb = 0.5 * e01, cd_ = 1.0 + 0.5 * e11;  // C = P0 (already applied)
+                    double ta = 1.0, tb = 0.0, td = 1.0;                                 // T = product of later P_j
+                    const double n00 = sqrt(st[2]), n10 = sqrt(st[3]), n01 = sqrt(st[4]), n11 = sqrt(st[5]);
+                    while (it_done < p.max_iter) {
+                        // E = C^-1 M C^-T - I for upper-triangular C = [[ca, cb], [0, cd_]]
+                        const double ia = 1.0 / ca, id = 1.0 / cd_, ib = -cb * ia * id;
+                        const double r00 = ia * m00 + ib * m01, r01 = ia * m01 + ib * m11;  // row 0 of C^-1 M
+                        const double r11 = id * m11;                                          // row 1: (id*m01, id*m11)
+                        const double E00 = r00 * ia + r01 * ib - 1.0, E01 = r01 * id, E11 = r11 * id - 1.0;
+                        const double pa = 0.5 * E00, pb = 0.5 * E01, pd = 0.5 * E11;  // P_j - I
+                        // max |G_j (P_j - I)| with the column maxima of G at tail entry
+                        const double d0 = fmax(n00, n10) * fabs(pa);
+                        const double d1 = fmax(n00 * fabs(pb) + n01 * fabs(pd), n10 * fabs(pb) + n11 * fabs(pd));
+                        // T <- T P_j, C <- C P_j
+                        tb = ta * pb + tb * (1.0 + pd); ta *= 1.0 + pa; td *= 1.0 + pd;
+                        cb = ca * pb + cb * (1.0 + pd); ca *= 1.0 + pa; cd_ *= 1.0 + pd;
+                        ++it_done;
+                        if (fmax(d0, d1) < p.tol) {
+                            converged = true;
+                            break;
                         }
-                        const double ssum = eps * (1.0 - ldexp(1.0, -m));  // eps * sum_{q=1..m} 2^-q
-#pragma unroll
-                        for (int q = 0; q < FPT; ++q) {
-                            g01[q].x += ssum * g00[q].x; g01[q].y += ssum * g00[q].y;
-                            g11[q].x += ssum * g10[q].x; g11[q].y += ssum * g10[q].y;
-                        }
-                        it_done += m;
-                        converged = d < p.tol;
-                        break;
                     }
+#pragma unroll
+                    for (int q = 0; q < FPT; ++q) {
+                        g01[q].x = g00[q].x * tb + g01[q].x * td; g01[q].y = g00[q].y * tb + g01[q].y * td;
+                        g11[q].x = g10[q].x * tb + g11[q].x * td; g11[q].y = g10[q].y * tb + g11[q].y * td;
+                        g00[q].x *= ta; g00[q].y *= ta; g10[q].x *= ta; g10[q].y *= ta;
+                    }
+                    break;
                 }
             }
             if (!converged) flag |= SC_FLAG_NOT_CONVERGED;

@@ -61,19 +61,20 @@ __device__ __forceinline__ void block_sum(double* v, double* red) {
     }
 }
 
-__device__ __forceinline__ void block_max3(double (&v)[3], double* red) {
+template <int NV>
+__device__ __forceinline__ void block_maxn(double (&v)[NV], double* red) {
 #pragma unroll
-    for (int q = 0; q < 3; ++q)
+    for (int q = 0; q < NV; ++q)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[q] = fmax(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();
     if (lane == 0)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) red[q * kWarps + warp] = v[q];
+        for (int q = 0; q < NV; ++q) red[q * kWarps + warp] = v[q];
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < NV; ++q) {
         double m = red[q * kWarps];
 #pragma unroll
         for (int w = 1; w < kWarps; ++w) m = fmax(m, red[q * kWarps + w]);
