@@ -139,11 +139,16 @@ int sc_wilson2(const void* csm_c128, int64_t B, int nfft, double tolerance, int 
  *           the lag-0 coefficient and then zeroes the lower triangle, mpd.py:132-138, so the lag-0
  *           off-diagonal residual halves per iteration), the remaining iterations are summed in
  *           closed form up to the iterate the reference stops at; out_iters reports that iterate.
+ *  mixed_precision  1 (hermitian_half only, needs twiddle_c64 = c64 [nfft]): the first iterations, while
+ *           max|dG| is still above 2e-3 of |G|, run in fp32 on the row-scaled problem; every later
+ *           iteration, the stopping test and the Granger epilogue are fp64.  Moves the result by
+ *           ~5e-7 relative (the fp32-born CSM already carries 3e-7).  0: fp64 throughout.
  *  out_iters/out_flags  int32 [n_pairs][B] or NULL */
 int sc_granger_pairwise(const void* csm_c64, const float* power, int64_t B, int F, int nfft, int hermitian_half,
                         int64_t S, const int* pairs, int64_t n_pairs, double tolerance, int max_iterations,
-                        int tail_extrapolation, const void* twiddle_c128, float* out_gc, int* out_iters,
-                        int* out_flags, void* workspace, int64_t workspace_bytes, void* stream);
+                        int tail_extrapolation, int mixed_precision, const void* twiddle_c128,
+                        const void* twiddle_c64, float* out_gc, int* out_iters, int* out_flags, void* workspace,
+                        int64_t workspace_bytes, void* stream);
 int64_t sc_wilson_workspace_bytes(int nfft);
 
 #ifdef __cplusplus

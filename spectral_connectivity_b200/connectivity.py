@@ -209,7 +209,8 @@ class Connectivity:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._reduce_group)
         return t
 
-    def compute(self, measures, pairs=None, tolerance=1e-8, max_iterations=60, tail_extrapolation=True):
+    def compute(self, measures, pairs=None, tolerance=1e-8, max_iterations=60, tail_extrapolation=True,
+                mixed_precision=True):
         """Compute several measures in ONE streaming pass over window chunks.
 
         ``measures``: iterable of names from ``MEASURES``.  Returns {name: array}.  Per chunk
@@ -219,7 +220,9 @@ class Connectivity:
         ``tail_extrapolation`` (Granger, real-series path only): sum the geometric tail of the
         reference's Wilson iteration in closed form instead of iterating through it -- same
         stopping iterate, same iteration count, results equal to ~1e-7 relative.
-        ``False`` runs every iteration like the reference."""
+        ``False`` runs every iteration like the reference.  ``mixed_precision`` (same path): the
+        first Wilson iterations (update still > 2e-3 of |G|) run in fp32, the rest in fp64; moves
+        results by ~5e-7 relative.  ``False`` keeps the factorisation in fp64 throughout."""
         lib = _lib.load()
         measures = list(measures)
         for name in measures:
@@ -275,6 +278,7 @@ class Connectivity:
             ws_bytes = lib.sc_wilson_workspace_bytes(nfft)
             gr_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             tw128 = twiddles(nfft, torch.complex128, dev)
+            tw64 = twiddles(nfft, torch.complex64, dev)
             it_all = torch.zeros((n_pairs, n_batch), dtype=torch.int32, device=dev)
             fl_all = torch.zeros((n_pairs, n_batch), dtype=torch.int32, device=dev)
 
@@ -354,7 +358,8 @@ class Connectivity:
                     rc = lib.sc_granger_pairwise(_lib.ptr(csm), _lib.ptr(power), nb, n_freq, nfft,
                                                  1 if self._hermitian else 0, n_sig, _lib.ptr(pair_t), n_pairs,
                                                  float(tolerance), int(max_iterations), 1 if tail_extrapolation else 0,
-                                                 _lib.ptr(tw128), _lib.ptr(dst),
+                                                 1 if mixed_precision else 0, _lib.ptr(tw128), _lib.ptr(tw64),
+                                                 _lib.ptr(dst),
                                                  _lib.ptr(it_c), _lib.ptr(fl_c), _lib.ptr(gr_ws), ws_bytes, st)
                     _lib.check(rc, "sc_granger_pairwise")
                 it_all[:, b0:b1] = it_c
@@ -488,17 +493,20 @@ class Connectivity:
         """connectivity.py:1129-1159."""
         return self._one("pairwise_phase_consistency")
 
-    def pairwise_spectral_granger_prediction(self, tolerance=1e-8, max_iterations=60, tail_extrapolation=True):
+    def pairwise_spectral_granger_prediction(self, tolerance=1e-8, max_iterations=60, tail_extrapolation=True,
+                                             mixed_precision=True):
         """Spectral Granger prediction for every signal pair; [..., i, j] is the influence
         j -> i (connectivity.py:1161-1191)."""
         return self._one("pairwise_spectral_granger_prediction", tolerance=tolerance,
-                         max_iterations=max_iterations, tail_extrapolation=tail_extrapolation)
+                         max_iterations=max_iterations, tail_extrapolation=tail_extrapolation,
+                         mixed_precision=mixed_precision)
 
     def subset_pairwise_spectral_granger_prediction(self, pairs, tolerance=1e-8, max_iterations=60,
-                                                    tail_extrapolation=True):
+                                                    tail_extrapolation=True, mixed_precision=True):
         """connectivity.py:1193-1213."""
         return self._one("pairwise_spectral_granger_prediction", pairs=pairs, tolerance=tolerance,
-                         max_iterations=max_iterations, tail_extrapolation=tail_extrapolation)
+                         max_iterations=max_iterations, tail_extrapolation=tail_extrapolation,
+                         mixed_precision=mixed_precision)
 
     def conditional_spectral_granger_prediction(self):
         raise NotImplementedError  # connectivity.py:1215-1219

@@ -17,6 +17,9 @@ namespace {
 
 using namespace scw;
 
+constexpr int kMaxF32Iters = 12;     // fp32 phase never runs longer than this
+constexpr float kSwitch = 2e-3f;     // hand over to fp64 when max |dG'| (scaled units, |G'| ~ 1) drops below
+
 struct CtaSync {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
@@ -62,7 +65,7 @@ template <> struct RealOps<float> {
 template <typename R, int FPT, typename FFT>
 __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[FPT], cx<R> (&g10)[FPT],
                                                cx<R> (&g11)[FPT], const float (&s00)[FPT], const float (&s11)[FPT],
-                                               const float2 (&s01)[FPT], R sscale, cx<R>* ZA, cx<R>* ZB,
+                                               const float2 (&s01)[FPT], R k00, R k11, R k01, cx<R>* ZA, cx<R>* ZB,
                                                const ScFftPlan& plan, const cx<R>* tw, int N, int fnn,
                                                R* lag0, R (&stat)[6]) {
     // ---- linear predictor (mpd.py:218-224), Hermitian: b00, b11 real, b10 = conj(b01) ----
@@ -75,8 +78,8 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
             const cx<R> idet = cmake<R>(det.x * dn, -det.y * dn);
             const cx<R> u0 = cmul(g11[q], idet), u1 = cmul(g01[q], idet);   // row 0 of G^-1 = (u0, -u1)
             const cx<R> v0 = cmul(g10[q], idet), v1 = cmul(g00[q], idet);   // row 1 of G^-1 = (-v0, v1)
-            const R a = (R)s00[q] * sscale, d = (R)s11[q] * sscale;
-            const cx<R> c = cmake<R>((R)s01[q].x * sscale, (R)s01[q].y * sscale);
+            const R a = (R)s00[q] * k00, d = (R)s11[q] * k11;
+            const cx<R> c = cmake<R>((R)s01[q].x * k01, (R)s01[q].y * k01);
             // M = Ginv S Ginv^H with rows r0 = (u0, -u1), r1 = (-v0, v1)
             // t = r S : t0 = r.x*a + r.y*conj(c), t1 = r.x*c + r.y*d
             const cx<R> cc = cconj(c);
@@ -169,10 +172,15 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
     const int N = p.nfft;
     const int fnn = N / 2 + 1;
     __shared__ double lag0_sh[3];
+    __shared__ float lag0f_sh[3];
     cd* ZA = reinterpret_cast<cd*>(smem_raw);
     cd* ZB = ZA + 2 * (size_t)N;
     cd* tws = ZB + 2 * (size_t)N;
+    cx<float>* twsf = reinterpret_cast<cx<float>*>(tws + FFT::tw_entries(N));
+    cx<float>* ZAf = reinterpret_cast<cx<float>*>(ZA);  // the fp32 phase reuses the fp64 buffers
+    cx<float>* ZBf = ZAf + 2 * (size_t)N;
     FFT::template fill<double>(tws, p.tw, N);
+    if (p.tw32) FFT::template fill<float>(twsf, p.tw32, N);
     __syncthreads();
     const long long npairs = p.n_pairs;
     const long long nprob = p.B * npairs;
@@ -220,9 +228,43 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
         }
         if (!flag) {
             bool converged = false;
-            for (int it = 0; it < p.max_iter && !converged; ++it) {
+            int it0 = 0;
+            if (p.tw32 && p.mixed) {
+                // ---- fp32 phase: the same iteration on the row-scaled problem S' = D S D, G' = D G with
+                // D = diag(a00, a11)^-1/2 (the iteration is equivariant under a left diagonal scaling, so
+                // this only keeps every intermediate O(1) in single precision).  It stops as soon as the
+                // update falls below kSwitch (relative), after which fp64 takes over: the fixed point and
+                // the stopping test are decided entirely in fp64.
+                const float r0 = (float)(1.0 / sqrt(a00)), r1 = (float)(1.0 / sqrt(a11));
+                cx<float> f00[FPT], f01[FPT], f10[FPT], f11[FPT];
+#pragma unroll
+                for (int q = 0; q < FPT; ++q) {
+                    f00[q] = cmake<float>((float)l00 * r0, 0.f); f01[q] = cmake<float>((float)l10 * r0, 0.f);
+                    f10[q] = cmake<float>(0.f, 0.f);             f11[q] = cmake<float>((float)l11 * r1, 0.f);
+                }
+                const int cap = p.max_iter < kMaxF32Iters ? p.max_iter : kMaxF32Iters;
+                for (; it0 < cap; ++it0) {
+                    float stf[6];
+                    herm_iteration<float, FPT, FFT>(f00, f01, f10, f11, s00, s11, s01, r0 * r0, r1 * r1, r0 * r1, ZAf, ZBf,
+                                                    p.plan, twsf, N, fnn, lag0f_sh, stf);
+                    double e2 = stf[0];
+                    const float errf = sqrtf((float)block_max(e2, red));  // also fences the buffers
+                    if (errf < kSwitch) {
+                        ++it0;
+                        break;
+                    }
+                }
+                const double u0 = sqrt(a00), u1 = sqrt(a11);
+#pragma unroll
+                for (int q = 0; q < FPT; ++q) {
+                    g00[q] = cmake<double>(f00[q].x * u0, f00[q].y * u0); g01[q] = cmake<double>(f01[q].x * u0, f01[q].y * u0);
+                    g10[q] = cmake<double>(f10[q].x * u1, f10[q].y * u1); g11[q] = cmake<double>(f11[q].x * u1, f11[q].y * u1);
+                }
+                it_done = it0;
+            }
+            for (int it = it0; it < p.max_iter && !converged; ++it) {
                 double st[6];
-                herm_iteration<double, FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, 1.0, ZA, ZB, p.plan, tws, N, fnn,
+                herm_iteration<double, FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, 1.0, 1.0, 1.0, ZA, ZB, p.plan, tws, N, fnn,
                                                  lag0_sh, st);
                 block_maxn<6>(st, red);  // also fences ZA/ZB reuse
                 const double err = sqrt(st[0]);
@@ -327,11 +369,12 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
     }
 }
 
-size_t herm_smem(int nfft) { return (size_t)5 * nfft * sizeof(cd); }  // ZA, ZB (2 sequences each), twiddles
+size_t herm_smem(int nfft) { return (size_t)5 * nfft * sizeof(cd) + (size_t)nfft * 8; }  // ZA, ZB, twiddles (f64 + f32)
 
 template <int FPT, typename FFT>
 int herm_launch(W2Params& p, cudaStream_t st) {
-    const size_t smem = (size_t)(4 * p.nfft + FFT::tw_entries(p.nfft)) * sizeof(cd);
+    const size_t smem = (size_t)(4 * p.nfft + FFT::tw_entries(p.nfft)) * sizeof(cd) +
+                        (size_t)FFT::tw_entries(p.nfft) * sizeof(cx<float>);
     if (smem > 48 * 1024)
         SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));

@@ -8,6 +8,8 @@
 // TS real series are packed two-per-complex-FFT, transformed by the CTA-cooperative Stockham
 // FFT (fft_device.cuh), unpacked to half (or full) spectra and stored with the signal axis
 // fastest, so the CSM stage reads [F][2][R][S] tiles directly.
+#include <type_traits>
+
 #include "fft_device.cuh"
 #include "sc_common.cuh"
 
@@ -33,8 +35,14 @@ struct MtParams {
     ScFftPlan plan;
 };
 
-template <int TS, bool WS>
-__global__ void __launch_bounds__(kThreads) mt_fft_kernel(const MtParams p) {
+struct CtaSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct DynPlan {};  // runtime plan (any nfft)
+
+template <int TS, bool WS, typename PLAN>
+__global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtParams p) {
+    constexpr bool STATIC = !std::is_same<PLAN, DynPlan>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = TS / 2;  // complex FFTs per taper
     const int n = p.n, nfft = p.nfft;
@@ -56,8 +64,10 @@ __global__ void __launch_bounds__(kThreads) mt_fft_kernel(const MtParams p) {
         bufB = bufA + (size_t)NP * nfft;
         cx<float>* tws = bufB + (size_t)NP * nfft;
         tile = reinterpret_cast<float*>(tws + nfft);
-        for (int q = threadIdx.x; q < nfft; q += kThreads) tws[q] = p.tw[q];
+        if constexpr (STATIC) ScStaticFft<float, PLAN>::fill(tws, p.tw, threadIdx.x, kThreads);
+        else for (int q = threadIdx.x; q < nfft; q += kThreads) tws[q] = p.tw[q];
         tw = tws;
+        __syncthreads();
     }
 
     for (long long item = blockIdx.x; item < total; item += gridDim.x) {
@@ -137,7 +147,11 @@ __global__ void __launch_bounds__(kThreads) mt_fft_kernel(const MtParams p) {
                 bufA[(size_t)pp * nfft + j] = z;
             }
             __syncthreads();
-            const cx<float>* res = sc_cta_fft<float>(bufA, bufB, NP, nfft, p.plan, tw, false);
+            const cx<float>* res;
+            if constexpr (STATIC)
+                res = ScStaticFft<float, PLAN>::template run<NP>(bufA, bufB, tw, false, threadIdx.x, kThreads, CtaSync());
+            else
+                res = sc_cta_fft<float>(bufA, bufB, NP, nfft, p.plan, tw, false);
 
             // ---- unpack the two real spectra and store -----------------------
             const long long wo = p.w_out0 + wl;
@@ -194,11 +208,12 @@ int mt_pick_ts(int n, int nfft) {
     return 0;  // workspace mode
 }
 
-template <int TS, bool WS>
+template <int TS, bool WS, typename PLAN = DynPlan>
 int mt_launch(const MtParams& p, size_t smem, long long grid, cudaStream_t st) {
     if (smem > 48 * 1024)
-        SC_CUDA_OK(cudaFuncSetAttribute(mt_fft_kernel<TS, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mt_fft_kernel<TS, WS><<<(unsigned)grid, kThreads, smem, st>>>(p);
+        SC_CUDA_OK(cudaFuncSetAttribute(mt_fft_kernel<TS, WS, PLAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    mt_fft_kernel<TS, WS, PLAN><<<(unsigned)grid, kThreads, smem, st>>>(p);
     SC_LAUNCH_OK();
     return SC_OK;
 }
@@ -278,6 +293,8 @@ extern "C" int sc_mt_fft(const float* x, int64_t N, int64_t T, int64_t S, const 
     const size_t smem = mt_smem_bytes(ts, n, nfft);
     const long long maxgrid = 1LL << 30;
     const long long grid = total < maxgrid ? total : maxgrid;
+    if (ts == 8 && nfft == 1000) return mt_launch<8, false, ScPlan1000>(p, smem, grid, st);
+    if (ts == 8 && nfft == 120) return mt_launch<8, false, ScPlan120>(p, smem, grid, st);
     switch (ts) {
         case 8: return mt_launch<8, false>(p, smem, grid, st);
         case 4: return mt_launch<4, false>(p, smem, grid, st);

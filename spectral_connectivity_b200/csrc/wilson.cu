@@ -296,9 +296,9 @@ extern "C" int sc_wilson2(const void* csm_c128, int64_t B, int nfft, double tole
 
 extern "C" int sc_granger_pairwise(const void* csm_c64, const float* power, int64_t B, int F, int nfft,
                                    int hermitian_half, int64_t S, const int* pairs, int64_t n_pairs, double tolerance,
-                                   int max_iterations, int tail_extrapolation, const void* twiddle_c128,
-                                   float* out_gc, int* out_iters, int* out_flags, void* workspace,
-                                   int64_t workspace_bytes, void* stream) {
+                                   int max_iterations, int tail_extrapolation, int mixed_precision,
+                                   const void* twiddle_c128, const void* twiddle_c64, float* out_gc, int* out_iters,
+                                   int* out_flags, void* workspace, int64_t workspace_bytes, void* stream) {
     SC_CHECK_ARG(csm_c64 && power && twiddle_c128 && out_gc, "sc_granger_pairwise: null pointer");
     SC_CHECK_ARG(B > 0 && nfft > 0 && S >= 2 && max_iterations >= 0, "sc_granger_pairwise: bad size");
     SC_CHECK_ARG(hermitian_half ? F == nfft / 2 + 1 : F == nfft,
@@ -310,6 +310,8 @@ extern "C" int sc_granger_pairwise(const void* csm_c64, const float* power, int6
     p.pairs = pairs; p.n_pairs = n_pairs; p.tol = tolerance; p.max_iter = max_iterations;
     p.tw = reinterpret_cast<const cd*>(twiddle_c128); p.out = out_gc; p.iters = out_iters; p.flags = out_flags;
     p.tail = tail_extrapolation ? 1 : 0;
+    p.mixed = (mixed_precision && twiddle_c64) ? 1 : 0;
+    p.tw32 = reinterpret_cast<const cx<float>*>(twiddle_c64);
     if (hermitian_half && sc_granger_herm_supported(nfft)) return sc_granger_herm_launch(p, stream);
     return w2_launch<1>(p, B * n_pairs, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }

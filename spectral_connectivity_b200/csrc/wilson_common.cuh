@@ -28,6 +28,8 @@ struct W2Params {
     unsigned char* ws;
     int use_smem;
     int tail;  // 1: sum the geometric tail of the reference iteration in closed form (Hermitian kernel)
+    int mixed; // 1: first iterations in fp32 on the row-scaled problem (Hermitian kernel, needs tw32)
+    const cx<float>* tw32;
     ScFftPlan plan;
 };
 

@@ -257,19 +257,22 @@ def test_config1_full(sc):
     assert np.abs(gpu_it.ravel() - np.array(its).ravel()).max() <= 1
 
 
-@pytest.mark.parametrize("tail", [False, True])
-def test_granger_tail_extrapolation_matches_reference_iteration(sc, tail):
+@pytest.mark.parametrize("tail,mixed", [(False, False), (True, False), (True, True), (False, True)])
+def test_granger_tail_extrapolation_matches_reference_iteration(sc, tail, mixed):
     """cfg-4-shaped window (1 s @ 1 kHz, 7 tapers, 64 trials): Granger values and the Wilson iteration
     count per (pair, window) must match the oracle with and without the closed-form tail."""
     fs = 1000.0
     x = O.synthetic_series(2000, 64, 6, fs, seed=20261021)
     m = sc.Multitaper(x, sampling_frequency=fs, time_halfbandwidth_product=4, time_window_duration=1.0)
     c = sc.Connectivity.from_multitaper(m)
-    got = c.pairwise_spectral_granger_prediction(tail_extrapolation=tail)
+    got = c.pairwise_spectral_granger_prediction(tail_extrapolation=tail, mixed_precision=mixed)
     n, step, nfft = O.window_geometry(2000, fs, 1.0)
     coef = O.multitaper_fft(x.astype(np.float32).astype(np.float64), fs, O.dpss_tapers(n, 4, 7, fs), n, step, nfft)
     ref, its = O.pairwise_granger(O.expected_csm(coef), O.power(coef), return_iterations=True)
-    assert_parity(got, ref, TOL, f"granger tail={tail}")
+    assert_parity(got, ref, TOL, f"granger tail={tail} mixed={mixed}")
+    # the accelerated modes must stay within 2e-6 (scale-normalised) of the plain fp64 iteration
+    plain = c.pairwise_spectral_granger_prediction(tail_extrapolation=False, mixed_precision=False)
+    assert np.nanmax(np.abs(got - plain)) / np.nanmax(np.abs(plain)) < 2e-6
     gpu_it = c.last_granger_iterations.cpu().numpy()  # [pairs][windows]
     assert np.abs(gpu_it - np.array(its)).max() <= 1
     assert (gpu_it == np.array(its)).mean() > 0.9
@@ -279,9 +282,9 @@ def test_granger_tail_extrapolation_matches_reference_iteration(sc, tail):
 def test_granger_max_iterations_flag(sc):
     fs = 1000.0
     x = O.synthetic_series(1000, 8, 3, fs, seed=2)
-    for tail in (False, True):
+    for tail, mixed in ((False, False), (True, True)):
         c = sc.Connectivity.from_multitaper(sc.Multitaper(x, fs, 4, time_window_duration=1.0))
-        c.pairwise_spectral_granger_prediction(max_iterations=5, tail_extrapolation=tail)
+        c.pairwise_spectral_granger_prediction(max_iterations=5, tail_extrapolation=tail, mixed_precision=mixed)
         assert int(c.last_granger_iterations.max()) <= 5
         assert int((c.last_granger_flags & 1).sum()) == 3  # all three pairs hit the iteration cap
 
