@@ -1,14 +1,411 @@
-// Tensor-core (tcgen05) cross-spectral matrix GEMM -- placeholder until the UMMA kernel lands.
+// Tensor-core cross-spectral matrix: C(b,f) = scale * sum_r X_r X_r^H on tcgen05 (sm_100a).
+//
+// Replaces the same reference code as csm.cu (connectivity.py:447-526, the k=1 batched matmul of
+// :1799-1822 plus the xp.mean of :67-75) for SC_CSM_CROSS when S is large enough to fill a
+// 128x128 UMMA tile.  Per (b, f) the planar coefficients are two real [R][S] slabs (Re, Im) with
+// the signal axis contiguous, i.e. MN-major operands:
+//
+//     Re C = Ar Ar^T + Ai Ai^T          Im C = Ai Ar^T - Ar Ai^T
+//
+// so one complex tile is four real 128x128xR GEMMs on the same four operand slabs; the minus
+// sign is the instruction descriptor's negate-A bit.  fp32 accuracy comes from the 3xTF32 split
+// x = hi + lo (hi = tf32 truncation, lo = x - hi): hi*hi + hi*lo + lo*hi, the dropped lo*lo term
+// is 2^-22 relative.  Only upper-triangular tiles are computed; the epilogue writes the tile and
+// its conjugate transpose.
+//
+// Warp-specialised persistent kernel, one CTA per SM:
+//   warp 0      TMA producer: 4-D tensor map {32 s, R, S/32, B*F*2} with 128B swizzle; a box
+//               {32, KC, 4, 1} lands as [4][KC][32 f32] = the canonical SWIZZLE_128B MN-major atom
+//               layout of the UMMA shared-memory descriptor; rows beyond R are zero-filled
+//   warps 2-5   converter: split the landed fp32 slab into hi (in place) and lo (mirror buffer)
+//   warp 1      MMA issuer: 12 tcgen05.mma.kind::tf32 (M=128, N=128, K=8) per K-step into two
+//               TMEM accumulators (Re, Im), double-buffered across tiles (4 x 128 = 512 columns)
+//   warps 6-9   epilogue: tcgen05.ld 32 columns at a time, scale, store C and conj(C)^T
+// Pipelines: smem ring (full_raw -> full_cvt -> empty) and TMEM ring (tmem_full/tmem_empty), all
+// mbarriers.  Every spin is bounded and traps, so a protocol bug cannot hang the device.
+#include <cuda.h>
+
 #include "sc_common.cuh"
 
+namespace {
+
+constexpr int TM = 128;                      // tile rows (signal i)
+constexpr int TN = 128;                      // tile cols (signal j)
+constexpr int KC = 16;                       // observations per smem stage
+constexpr int STAGES = 3;
+constexpr int SLAB = 4 * KC * 128;           // [4 groups of 32 signals][KC][128 B] = 8 KB
+constexpr int STAGE_RAW = 4 * SLAB;          // Ar_I, Ai_I, Ar_J, Ai_J
+constexpr int STAGE_BYTES = 2 * STAGE_RAW;   // + the lo mirror
+constexpr int NTHREADS = 320;
+constexpr int CVT_THREADS = 128;
+constexpr int EPI_THREADS = 128;
+constexpr uint32_t TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (spin > (1u << 28)) __trap();  // watchdog: a broken pipeline must not hang the GPU
+    }
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// shared-memory matrix descriptor, MN-major, SWIZZLE_128B (bit layout: cute/arch/mma_sm100_desc.hpp):
+// start address>>4 [0,14), leading byte offset>>4 [16,30) = stride between 32-element MN groups,
+// stride byte offset>>4 [32,46) = stride between 8-row K groups, version=1 [46,48), layout=2 [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    constexpr uint64_t LBO = (KC * 128) >> 4;
+    constexpr uint64_t SBO = 1024 >> 4;
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (LBO << 16) | (SBO << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// instruction descriptor: D=f32, A=B=tf32, both MN-major, M=128, N=128; optional negate-A
+__host__ __device__ constexpr uint32_t umma_idesc(bool neg_a) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((neg_a ? 1u : 0u) << 13) | (1u << 15) | (1u << 16) |
+           ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+struct TcParams {
+    long long BF, R, S;
+    float scale;
+    float2* out;
+    int ntile;       // ceil(S / 128)
+    long long ntiles;  // BF * ntile*(ntile+1)/2
+};
+
+__device__ __forceinline__ void decode_tile(long long t, int ntile, long long& bf, int& ti, int& tj) {
+    const int npair = ntile * (ntile + 1) / 2;
+    bf = t / npair;
+    int pidx = (int)(t % npair);
+    ti = 0;
+    while (pidx >= ntile - ti) {
+        pidx -= ntile - ti;
+        ++ti;
+    }
+    tj = ti + pidx;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) csm_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_raw[STAGES], full_cvt[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t tmem_base_sh;
+
+    unsigned char* stage_base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = (int)((p.R + KC - 1) / KC);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_raw[s], 1);
+            mbar_init(&full_cvt[s], CVT_THREADS);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], EPI_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+                long long bf;
+                int ti, tj;
+                decode_tile(t, p.ntile, bf, ti, tj);
+                const bool diag = ti == tj;
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* dst = stage_base + (size_t)stage * STAGE_BYTES;
+                    mbar_expect_tx(&full_raw[stage], (diag ? 2 : 4) * SLAB);
+                    const int plane = (int)(bf * 2);
+                    tma_load_4d(dst, &tmap, &full_raw[stage], 0, kc * KC, ti * 4, plane);
+                    tma_load_4d(dst + SLAB, &tmap, &full_raw[stage], 0, kc * KC, ti * 4, plane + 1);
+                    if (!diag) {
+                        tma_load_4d(dst + 2 * SLAB, &tmap, &full_raw[stage], 0, kc * KC, tj * 4, plane);
+                        tma_load_4d(dst + 3 * SLAB, &tmap, &full_raw[stage], 0, kc * KC, tj * 4, plane + 1);
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            constexpr uint32_t idesc = umma_idesc(false), idesc_neg = umma_idesc(true);
+            for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+                long long bf;
+                int ti, tj;
+                decode_tile(t, p.ntile, bf, ti, tj);
+                const bool diag = ti == tj;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_re = tmem_base + (uint32_t)acc * 256u;
+                const uint32_t d_im = d_re + 128u;
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(&full_cvt[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t hi = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
+                    const uint32_t lo = hi + STAGE_RAW;
+                    const uint32_t boff = diag ? 0u : 2u * SLAB;
+#pragma unroll
+                    for (int ks = 0; ks < KC / 8; ++ks) {
+                        const uint32_t ko = (uint32_t)ks * 1024u;
+                        const uint64_t arh = umma_desc(hi + ko), aih = umma_desc(hi + SLAB + ko);
+                        const uint64_t arl = umma_desc(lo + ko), ail = umma_desc(lo + SLAB + ko);
+                        const uint64_t brh = umma_desc(hi + boff + ko), bih = umma_desc(hi + boff + SLAB + ko);
+                        const uint64_t brl = umma_desc(lo + boff + ko), bil = umma_desc(lo + boff + SLAB + ko);
+                        const uint32_t first = (kc | ks) ? 1u : 0u;
+                        // Re += Ar Br^T + Ai Bi^T   (hi*hi + hi*lo + lo*hi)
+                        umma_tf32(d_re, arh, brh, idesc, first);
+                        umma_tf32(d_re, arh, brl, idesc, 1u);
+                        umma_tf32(d_re, arl, brh, idesc, 1u);
+                        umma_tf32(d_re, aih, bih, idesc, 1u);
+                        umma_tf32(d_re, aih, bil, idesc, 1u);
+                        umma_tf32(d_re, ail, bih, idesc, 1u);
+                        // Im += Ai Br^T - Ar Bi^T
+                        umma_tf32(d_im, aih, brh, idesc, first);
+                        umma_tf32(d_im, aih, brl, idesc, 1u);
+                        umma_tf32(d_im, ail, brh, idesc, 1u);
+                        umma_tf32(d_im, arh, bih, idesc_neg, 1u);
+                        umma_tf32(d_im, arh, bil, idesc_neg, 1u);
+                        umma_tf32(d_im, arl, bih, idesc_neg, 1u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // stage reusable once these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== converter: fp32 -> (hi, lo) =====================
+        const int ct = threadIdx.x - 64;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+            long long bf;
+            int ti, tj;
+            decode_tile(t, p.ntile, bf, ti, tj);
+            const int nvec = (ti == tj ? 2 : 4) * SLAB / 16;
+            for (int kc = 0; kc < nk; ++kc) {
+                mbar_wait(&full_raw[stage], phase);
+                float4* raw = reinterpret_cast<float4*>(stage_base + (size_t)stage * STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(stage_base + (size_t)stage * STAGE_BYTES + STAGE_RAW);
+#pragma unroll 4
+                for (int idx = ct; idx < nvec; idx += CVT_THREADS) {
+                    const float4 v = raw[idx];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                    raw[idx] = h;
+                    lo[idx] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&full_cvt[stage]);
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+            long long bf;
+            int ti, tj;
+            decode_tile(t, p.ntile, bf, ti, tj);
+            const bool diag = ti == tj;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long i = (long long)ti * TM + q * 32 + lane;
+            const long long j0 = (long long)tj * TN;
+            float2* mat = p.out + bf * p.S * p.S;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+#pragma unroll 1
+            for (int c = 0; c < TN / 32; ++c) {
+                uint32_t re[32], im[32];
+                tmem_ld32(trow + c * 32, re);
+                tmem_ld32(trow + 128 + c * 32, im);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c == TN / 32 - 1) {
+                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&tmem_empty[acc]);
+                }
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    const long long j = j0 + c * 32 + u;
+                    const float2 v = make_float2(__uint_as_float(re[u]) * p.scale, __uint_as_float(im[u]) * p.scale);
+                    if (j < p.S) {
+                        if (i < p.S) mat[i * p.S + j] = v;
+                        if (!diag && i < p.S) mat[j * p.S + i] = make_float2(v.x, -v.y);  // coalesced across lanes
+                    }
+                }
+            }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+    return fn;
+}
+
+}  // namespace
+
 int sc_csm_tc_supported(int64_t R, int64_t S) {
-    (void)R; (void)S;
-    return 0;
+    static int disabled = -1;
+    if (disabled < 0) {
+        const char* e = getenv("SC_B200_DISABLE_TC");
+        disabled = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (disabled) return 0;
+    // S must tile into 32-signal TMA groups; below 96 signals a 128x128 UMMA tile is mostly padding
+    return S >= 96 && S % 32 == 0 && R >= 1 && get_encode() != nullptr;
 }
 
 int sc_csm_tc_launch(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, float scale, void* out,
                      cudaStream_t st) {
-    (void)xp; (void)B; (void)F; (void)R; (void)S; (void)scale; (void)out; (void)st;
-    sc_set_error("sc_csm: tensor-core path not built");
-    return SC_ERR_UNSUPPORTED;
+    SC_CHECK_ARG(xp && out, "sc_csm[tc]: null pointer");
+    SC_CHECK_ARG(B > 0 && F > 0 && R > 0 && S > 0 && S % 32 == 0, "sc_csm[tc]: unsupported shape");
+    SC_CHECK_ARG((reinterpret_cast<uintptr_t>(xp) & 15) == 0, "sc_csm[tc]: coefficients must be 16-byte aligned");
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        sc_set_error("sc_csm[tc]: cuTensorMapEncodeTiled unavailable");
+        return SC_ERR_UNSUPPORTED;
+    }
+    const long long planes = B * F * 2;
+    SC_CHECK_ARG(planes < (1LL << 31) && R < (1LL << 31), "sc_csm[tc]: batch too large for one tensor map");
+    CUtensorMap tmap;
+    const cuuint64_t gdim[4] = {32, (cuuint64_t)R, (cuuint64_t)(S / 32), (cuuint64_t)planes};
+    const cuuint64_t gstr[3] = {(cuuint64_t)S * 4, 128, (cuuint64_t)R * S * 4};  // bytes, dims 1..3
+    const cuuint32_t box[4] = {32, KC, 4, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(xp), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        sc_set_error("sc_csm[tc]: cuTensorMapEncodeTiled failed with %d (R=%lld S=%lld planes=%lld)", (int)cr,
+                     (long long)R, (long long)S, planes);
+        return SC_ERR_CUDA;
+    }
+    TcParams p;
+    p.BF = B * F; p.R = R; p.S = S; p.scale = scale; p.out = reinterpret_cast<float2*>(out);
+    p.ntile = (int)((S + TM - 1) / TM);
+    p.ntiles = p.BF * (long long)(p.ntile * (p.ntile + 1) / 2);
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+    SC_CUDA_OK(cudaFuncSetAttribute(csm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = sc_num_sms();
+    if (grid > p.ntiles) grid = p.ntiles;
+    csm_tc_kernel<<<(unsigned)grid, NTHREADS, smem, st>>>(tmap, p);
+    SC_LAUNCH_OK();
+    return SC_OK;
 }

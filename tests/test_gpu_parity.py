@@ -351,3 +351,31 @@ def test_window_sharding_equals_single_gpu(sc):
         assert cat.shape == ref[k].shape
         assert np.array_equal(np.isnan(cat), np.isnan(ref[k]))
         assert np.nanmax(np.abs(cat - ref[k])) == 0.0, k  # same kernels on the same windows: bit identical
+
+
+@pytest.mark.parametrize("n_sig,n_obs,n_bf", [(128, 16, 2), (128, 40, 3), (256, 448, 2), (96, 7, 5), (160, 33, 2), (512, 24, 1)])
+def test_csm_tensor_core_matches_simt_and_fp64(sc, n_sig, n_obs, n_bf):
+    """tcgen05 (3xTF32) cross-spectral matrix vs the SIMT fp32 kernel and a float64 einsum."""
+    from spectral_connectivity_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(n_sig + n_obs)
+    xp = torch.randn((n_bf, 1, 2, n_obs, n_sig), generator=g, device="cuda", dtype=torch.float32)
+    xp[..., ::3] *= 37.0  # uneven channel scales
+    out_tc = torch.full((n_bf, 1, n_sig, n_sig), float("nan"), dtype=torch.complex64, device="cuda")
+    out_simt = torch.empty_like(out_tc)
+    st = _lib.stream_ptr()
+    _lib.check(lib.sc_csm(_lib.ptr(xp), n_bf, 1, n_obs, n_sig, 1.0 / n_obs, _lib.CSM_CROSS, _lib.ptr(out_tc), st), "tc")
+    _lib.check(lib.sc_csm_simt(_lib.ptr(xp), n_bf, 1, n_obs, n_sig, 1.0 / n_obs, _lib.CSM_CROSS, _lib.ptr(out_simt), st),
+               "simt")
+    torch.cuda.synchronize()
+    z = torch.complex(xp[:, 0, 0].double(), xp[:, 0, 1].double())          # (bf, r, s)
+    ref = torch.einsum("bri,brj->bij", z, z.conj()) / n_obs
+    ref_np, tc_np, simt_np = ref.cpu().numpy(), out_tc[:, 0].cpu().numpy(), out_simt[:, 0].cpu().numpy()
+    assert not np.isnan(tc_np).any()
+    scale = np.abs(ref_np).max()
+    assert np.abs(simt_np - ref_np).max() / scale < 2e-6
+    assert np.abs(tc_np - ref_np).max() / scale < 2e-6, np.abs(tc_np - ref_np).max() / scale
+    # element-wise against each entry's own scale sqrt(P_i P_j) (what coherence divides by)
+    pw = np.sqrt(np.einsum("bii->bi", ref_np).real)
+    norm = pw[:, :, None] * pw[:, None, :]
+    assert (np.abs(tc_np - ref_np) / norm).max() < 5e-6
