@@ -124,27 +124,34 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
         for (int k = 0; k < p.K; ++k) {
             const float* h = p.tapers + (size_t)k * n;
             // ---- taper product, two real series per complex sequence --------
-            for (int idx = threadIdx.x; idx < NP * nfft; idx += kThreads) {
-                const int pp = idx % NP;
-                const int j = idx / NP;
-                cx<float> z = cmake<float>(0.f, 0.f);
-                if (j < ncopy) {
-                    const float hv = __ldg(h + j);
-                    float v0, v1;
-                    if (WS) {
+            if (WS) {
+                for (int idx = threadIdx.x; idx < NP * nfft; idx += kThreads) {
+                    const int pp = idx % NP;
+                    const int j = idx / NP;
+                    cx<float> z = cmake<float>(0.f, 0.f);
+                    if (j < ncopy) {
+                        const float hv = __ldg(h + j);
                         const float u = (j + 1.0f) / n;
-                        v0 = (s0 + 2 * pp < p.S) ? __ldg(xw + (long long)j * row + 2 * pp) : 0.f;
-                        v1 = (s0 + 2 * pp + 1 < p.S) ? __ldg(xw + (long long)j * row + 2 * pp + 1) : 0.f;
+                        float v0 = (s0 + 2 * pp < p.S) ? __ldg(xw + (long long)j * row + 2 * pp) : 0.f;
+                        float v1 = (s0 + 2 * pp + 1 < p.S) ? __ldg(xw + (long long)j * row + 2 * pp + 1) : 0.f;
                         v0 -= trend_a[2 * pp] * u + trend_b[2 * pp];
                         v1 -= trend_a[2 * pp + 1] * u + trend_b[2 * pp + 1];
-                    } else {
-                        const float2 v = *reinterpret_cast<const float2*>(tile + j * TS + 2 * pp);
-                        v0 = v.x;
-                        v1 = v.y;
+                        z = cmake<float>(v0 * hv, v1 * hv);
                     }
-                    z = cmake<float>(v0 * hv, v1 * hv);
+                    bufA[(size_t)pp * nfft + j] = z;
                 }
-                bufA[(size_t)pp * nfft + j] = z;
+            } else {
+                // one thread per sample j: the taper value is loaded once and applied to all TS series
+#pragma unroll 2
+                for (int j = threadIdx.x; j < nfft; j += kThreads) {
+                    const float hv = j < ncopy ? __ldg(h + j) : 0.f;
+                    const float* trow = tile + (size_t)(j < ncopy ? j : 0) * TS;
+#pragma unroll
+                    for (int pp = 0; pp < NP; ++pp) {
+                        const float2 v = *reinterpret_cast<const float2*>(trow + 2 * pp);
+                        bufA[(size_t)pp * nfft + j] = cmake<float>(v.x * hv, v.y * hv);
+                    }
+                }
             }
             __syncthreads();
             const cx<float>* res;
@@ -160,17 +167,35 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
                 const long long r = wo * p.map.rw + t * p.map.rt + k * p.map.rk;
                 float* out = reinterpret_cast<float*>(p.out);
                 const long long plane = p.R * p.S;
-                for (int idx = threadIdx.x; idx < p.nfo * 2 * TS; idx += kThreads) {
-                    const int s = idx % TS;
-                    const int c = (idx / TS) & 1;
-                    const int f = idx / (2 * TS);
-                    if (s0 + s >= p.S) continue;
-                    const cx<float> z1 = res[(size_t)(s >> 1) * nfft + f];
-                    const cx<float> z2 = res[(size_t)(s >> 1) * nfft + (f == 0 ? 0 : nfft - f)];
-                    float v;
-                    if ((s & 1) == 0) v = c == 0 ? (z1.x + z2.x) : (z1.y - z2.y);
-                    else v = c == 0 ? (z1.y + z2.y) : (z2.x - z1.x);
-                    out[((b * p.nfo + f) * 2 + c) * plane + r * p.S + s0 + s] = 0.5f * p.scale * v;
+                const float sc = 0.5f * p.scale;
+                if (TS % 4 == 0 && (p.S & 3) == 0 && s0 + TS <= p.S) {
+                    constexpr int QV = TS / 4 > 0 ? TS / 4 : 1;  // float4 stores per (f, plane) row
+                    for (int idx = threadIdx.x; idx < p.nfo * 2 * QV; idx += kThreads) {
+                        const int qv = idx % QV;
+                        const int c = (idx / QV) & 1;
+                        const int f = idx / (2 * QV);
+                        const int fm = f == 0 ? 0 : nfft - f;
+                        const cx<float> a1 = res[(size_t)(2 * qv) * nfft + f], a2 = res[(size_t)(2 * qv) * nfft + fm];
+                        const cx<float> b1 = res[(size_t)(2 * qv + 1) * nfft + f], b2 = res[(size_t)(2 * qv + 1) * nfft + fm];
+                        float4 v;
+                        if (c == 0) v = make_float4(a1.x + a2.x, a1.y + a2.y, b1.x + b2.x, b1.y + b2.y);
+                        else v = make_float4(a1.y - a2.y, a2.x - a1.x, b1.y - b2.y, b2.x - b1.x);
+                        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+                        *reinterpret_cast<float4*>(out + ((b * p.nfo + f) * 2 + c) * plane + r * p.S + s0 + 4 * qv) = v;
+                    }
+                } else {
+                    for (int idx = threadIdx.x; idx < p.nfo * 2 * TS; idx += kThreads) {
+                        const int s = idx % TS;
+                        const int c = (idx / TS) & 1;
+                        const int f = idx / (2 * TS);
+                        if (s0 + s >= p.S) continue;
+                        const cx<float> z1 = res[(size_t)(s >> 1) * nfft + f];
+                        const cx<float> z2 = res[(size_t)(s >> 1) * nfft + (f == 0 ? 0 : nfft - f)];
+                        float v;
+                        if ((s & 1) == 0) v = c == 0 ? (z1.x + z2.x) : (z1.y - z2.y);
+                        else v = c == 0 ? (z1.y + z2.y) : (z2.x - z1.x);
+                        out[((b * p.nfo + f) * 2 + c) * plane + r * p.S + s0 + s] = sc * v;
+                    }
                 }
             } else {
                 float2* out = reinterpret_cast<float2*>(p.out);
