@@ -428,6 +428,58 @@ def pairwise_granger(csm, total_power, pairs=None, tolerance=1e-8, max_iteration
 
 
 # --------------------------------------------------------------------------- #
+# MVAR family from the full-matrix Wilson factor
+# --------------------------------------------------------------------------- #
+def mvar_transfer_function(csm):
+    """Non-negative-frequency H from the full S x S factor (connectivity.py:567-574)."""
+    g = wilson(csm)
+    return _nonneg(transfer_function(g), -3), noise_covariance(g)
+
+
+def mvar_fourier_coefficients(h):
+    """Tikhonov-regularised inverse of H per (w, f) (connectivity.py:580-588)."""
+    lam = TIKHONOV * np.mean(np.real(np.conj(h) * h))
+    eye = np.eye(h.shape[-1], dtype=h.dtype)
+    return np.linalg.solve(h + lam * eye, eye)
+
+
+def _noise_variance(sigma):
+    return np.diagonal(sigma, axis1=-1, axis2=-2)[..., None, :, None]  # connectivity.py:1904-1925
+
+
+def directed_transfer_function(h):
+    """connectivity.py:1237-1266."""
+    inflow = np.sqrt(np.sum(np.abs(h) ** 2, axis=-1, keepdims=True))
+    return np.abs(h / inflow) ** 2
+
+
+def directed_coherence(h, sigma):
+    """connectivity.py:1268-1296."""
+    nv = _noise_variance(sigma)
+    inflow = np.sqrt(np.sum(nv * np.abs(h) ** 2, axis=-1, keepdims=True))
+    return np.sqrt(nv) * np.abs(h) ** 2 / inflow
+
+
+def partial_directed_coherence(a):
+    """connectivity.py:1298-1343."""
+    outflow = np.sqrt(np.sum(np.abs(a) ** 2, axis=-2, keepdims=True))
+    return np.abs(a / outflow) ** 2
+
+
+def generalized_partial_directed_coherence(a, sigma):
+    """connectivity.py:1345-1380."""
+    nv = _noise_variance(sigma)
+    outflow = np.sqrt(np.sum(np.abs(a) ** 2 / nv, axis=-2, keepdims=True))
+    return np.abs(a / np.sqrt(nv) / outflow) ** 2
+
+
+def direct_directed_transfer_function(h, a):
+    """connectivity.py:1382-1426 (inflow summed over sources AND frequencies)."""
+    inflow = np.sqrt(np.sum(np.abs(h) ** 2, axis=(-1, -3), keepdims=True))
+    return np.abs(h / inflow) * np.sqrt(partial_directed_coherence(a))
+
+
+# --------------------------------------------------------------------------- #
 # deterministic synthetic workloads (BASELINE.md section 3, SURVEY.md section 8d)
 # --------------------------------------------------------------------------- #
 CONFIGS = {

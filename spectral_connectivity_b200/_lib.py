@@ -31,6 +31,12 @@ SIGNATURES = {
     "sc_granger_pairwise": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int64, _P, c_int64, c_double, c_int,
                                     c_int, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "sc_wilson_workspace_bytes": (c_int64, [c_int]),
+    "sc_wilson": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, c_double, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
+    "sc_wilson_general_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
+    "sc_mvar_lag0": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
+    "sc_mvar_transfer": (c_int, [_P, _P, c_double, c_int64, c_int, c_int, c_int, _P, _P, _P]),
+    "sc_mvar_inverse": (c_int, [_P, c_double, c_int64, c_int, _P, _P]),
+    "sc_mvar_measure": (c_int, [c_int, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
 }
 
 # constants of include/sc_b200.h

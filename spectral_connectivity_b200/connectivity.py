@@ -514,31 +514,131 @@ class Connectivity:
     def blockwise_spectral_granger_prediction(self):
         raise NotImplementedError  # connectivity.py:1221-1224
 
-    # ---- rows SURVEY.md section 8(f) marks "next": not part of this round's hot path ----
+    # ---- MVAR family from the full-matrix Wilson factor ----------
+    _MVAR_MAX_SIGNALS = 32
+
+    def _mvar(self, tolerance=1e-8, max_iterations=60):
+        """Factor the expected CSM once and cache H (non-negative bins), the noise covariance and the
+        MVAR Fourier coefficients (the reference re-runs Wilson on every property access,
+        connectivity.py:567-588)."""
+        if getattr(self, "_mvar_cache", None) is not None:
+            return self._mvar_cache
+        if self.expectation_type not in _GRANGER_OK:
+            raise NotImplementedError(
+                f"MVAR measures with expectation_type='{self.expectation_type}' couple the Wilson convergence test "
+                "across a kept axis; only " + ", ".join(_GRANGER_OK) + " are supported.")
+        lib = _lib.load()
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        if n_sig > self._MVAR_MAX_SIGNALS:
+            raise NotImplementedError(
+                f"full-matrix Wilson factorisation on the device handles up to {self._MVAR_MAX_SIGNALS} signals "
+                f"(got {n_sig}); use pairwise_spectral_granger_prediction or a signal subset")
+        fnn = nfft // 2 + 1
+        herm = 1 if self._hermitian else 0
+        n_freq = fnn if self._hermitian else nfft
+        dev = self._device
+        kept = self._kept_dims()
+        n_batch = int(np.prod(kept)) if kept else 1
+        scale = 1.0 / self.n_observations
+        st = _lib.stream_ptr()
+        csm = torch.empty((n_batch, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
+        for b0, b1, xp, nr in self._chunks(n_freq):
+            _lib.check(lib.sc_csm(_lib.ptr(xp), b1 - b0, n_freq, nr, n_sig, scale, _lib.CSM_CROSS,
+                                  _lib.ptr(csm[b0:b1]), st), "sc_csm")
+            self._allreduce(csm[b0:b1])
+        csm = csm.to(torch.complex128)
+        g = torch.empty_like(csm)
+        iters = torch.zeros(n_batch, dtype=torch.int32, device=dev)
+        flags = torch.zeros(n_batch, dtype=torch.int32, device=dev)
+        tw = twiddles(nfft, torch.complex128, dev)
+        ws_bytes = lib.sc_wilson_general_workspace_bytes(n_batch, n_freq, n_sig)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.sc_wilson(_lib.ptr(csm), n_batch, n_freq, nfft, herm, n_sig, float(tolerance), int(max_iterations),
+                                 _lib.ptr(tw), _lib.ptr(g), _lib.ptr(iters), _lib.ptr(flags), _lib.ptr(ws), ws_bytes, st),
+                   "sc_wilson")
+        n_bad = int((flags & _lib.FLAG_NOT_CONVERGED).ne(0).sum())
+        if n_bad:
+            logger.warning(f"Maximum iterations reached. {n_batch - n_bad} of {n_batch} converged")
+        if int((flags & _lib.FLAG_NOT_SPD).ne(0).sum()):
+            logger.warning("Computing the initial conditions using the Cholesky failed; those factors are NaN.")
+        h0 = torch.empty((n_batch, n_sig, n_sig), dtype=torch.float64, device=dev)
+        _lib.check(lib.sc_mvar_lag0(_lib.ptr(g), n_batch, n_freq, nfft, herm, n_sig, _lib.ptr(h0), st), "sc_mvar_lag0")
+        lam = TIKHONOV_REGULARIZATION_FACTOR * float((h0 * h0).mean())  # over all windows, connectivity.py:1742-1746
+        h = torch.empty((n_batch, fnn, n_sig, n_sig), dtype=torch.complex128, device=dev)
+        sigma = torch.empty((n_batch, n_sig, n_sig), dtype=torch.float64, device=dev)
+        _lib.check(lib.sc_mvar_transfer(_lib.ptr(g), _lib.ptr(h0), lam, n_batch, n_freq, fnn, n_sig, _lib.ptr(h),
+                                        _lib.ptr(sigma), st), "sc_mvar_transfer")
+        lam_a = TIKHONOV_REGULARIZATION_FACTOR * float((h.real ** 2 + h.imag ** 2).mean())  # connectivity.py:585
+        a = torch.empty_like(h)
+        _lib.check(lib.sc_mvar_inverse(_lib.ptr(h), lam_a, n_batch * fnn, n_sig, _lib.ptr(a), st), "sc_mvar_inverse")
+        self.last_wilson_iterations, self.last_wilson_flags = iters, flags
+        self._mvar_cache = dict(g=g, h=h, sigma=sigma, a=a, kept=kept, n_batch=n_batch, fnn=fnn, n_sig=n_sig)
+        return self._mvar_cache
+
+    def _mvar_measure(self, code):
+        lib = _lib.load()
+        m = self._mvar()
+        nb, fnn, n_sig = m["n_batch"], m["fnn"], m["n_sig"]
+        out = torch.empty((nb, fnn, n_sig, n_sig), dtype=torch.float32, device=self._device)
+        scratch = torch.empty((nb, n_sig), dtype=torch.float64, device=self._device)
+        _lib.check(lib.sc_mvar_measure(code, _lib.ptr(m["h"]), _lib.ptr(m["a"]), _lib.ptr(m["sigma"]), nb, fnn, n_sig,
+                                       _lib.ptr(scratch), _lib.ptr(out), _lib.stream_ptr()), "sc_mvar_measure")
+        return self._finish(out.reshape(m["kept"] + (fnn, n_sig, n_sig)))
+
+    @property
+    def _minimum_phase_factor(self):
+        """connectivity.py:567-569 (half spectrum on the real-series path)."""
+        m = self._mvar()
+        return self._finish(m["g"].reshape(m["kept"] + tuple(m["g"].shape[1:])))
+
+    @property
+    def _transfer_function(self):
+        """connectivity.py:571-574, non-negative frequencies."""
+        m = self._mvar()
+        return self._finish(m["h"].reshape(m["kept"] + tuple(m["h"].shape[1:])))
+
+    @property
+    def _noise_covariance(self):
+        """connectivity.py:576-578."""
+        m = self._mvar()
+        return self._finish(m["sigma"].reshape(m["kept"] + tuple(m["sigma"].shape[1:])))
+
+    @property
+    def _MVAR_Fourier_coefficients(self):
+        """connectivity.py:580-588."""
+        m = self._mvar()
+        return self._finish(m["a"].reshape(m["kept"] + tuple(m["a"].shape[1:])))
+
+    def directed_transfer_function(self):
+        """connectivity.py:1237-1266."""
+        return self._mvar_measure(0)
+
+    def directed_coherence(self):
+        """connectivity.py:1268-1296."""
+        return self._mvar_measure(1)
+
+    def partial_directed_coherence(self, keep_cupy=False):
+        """connectivity.py:1298-1343."""
+        return self._mvar_measure(2)
+
+    def generalized_partial_directed_coherence(self):
+        """connectivity.py:1345-1380."""
+        return self._mvar_measure(3)
+
+    def direct_directed_transfer_function(self):
+        """connectivity.py:1382-1426."""
+        return self._mvar_measure(4)
+
+    # ---- rows still outside the device path (SURVEY.md section 8f rank 2 and "out of scope") ----
     def _next_round(self, name):
         raise NotImplementedError(
-            f"{name} is outside the round-1 hot-path scope (SURVEY.md section 8f); see DESIGN.md")
+            f"{name} is outside the current hot-path scope (SURVEY.md section 8f); see DESIGN.md")
 
     def canonical_coherence(self, group_labels):
         self._next_round("canonical_coherence")
 
     def global_coherence(self, max_rank=1):
         self._next_round("global_coherence")
-
-    def directed_transfer_function(self):
-        self._next_round("directed_transfer_function")
-
-    def directed_coherence(self):
-        self._next_round("directed_coherence")
-
-    def partial_directed_coherence(self, keep_cupy=False):
-        self._next_round("partial_directed_coherence")
-
-    def generalized_partial_directed_coherence(self):
-        self._next_round("generalized_partial_directed_coherence")
-
-    def direct_directed_transfer_function(self):
-        self._next_round("direct_directed_transfer_function")
 
     def group_delay(self, *args, **kwargs):
         self._next_round("group_delay")

@@ -23,8 +23,9 @@ def minimum_phase_decomposition(cross_spectral_matrix, tolerance=1e-8, max_itera
     (minimum_phase_decomposition.py:310-315).  Returns complex128 (NumPy for NumPy input, CUDA
     tensor for torch input); with ``return_info`` also (iterations, flags) int32 arrays.
 
-    Only 2x2 matrices (the pairwise-Granger case) run on the device this round; larger
-    matrices raise NotImplementedError.
+    2x2 matrices (the pairwise-Granger case) use the fused single-kernel path (``sc_wilson2``);
+    S x S matrices up to S = 32 use the batched multi-kernel path (``sc_wilson``); larger matrices
+    raise NotImplementedError.
     """
     lib = _lib.load()
     is_torch = isinstance(cross_spectral_matrix, torch.Tensor)
@@ -32,8 +33,11 @@ def minimum_phase_decomposition(cross_spectral_matrix, tolerance=1e-8, max_itera
     if csm.ndim not in (3, 4):
         raise NotImplementedError("only (n_time_points, n_fft_samples, S, S) or (n_fft_samples, S, S) inputs: "
                                   "extra kept axes couple the convergence test across problems")
-    if csm.shape[-1] != 2 or csm.shape[-2] != 2:
-        raise NotImplementedError("device Wilson factorisation currently handles 2x2 matrices only")
+    n_sig = csm.shape[-1]
+    if csm.shape[-2] != n_sig:
+        raise ValueError("cross_spectral_matrix must be square in its last two dimensions")
+    if n_sig > 32:
+        raise NotImplementedError("device Wilson factorisation currently handles up to 32 x 32 matrices")
     if not torch.cuda.is_available():
         raise RuntimeError("spectral_connectivity_b200 needs a CUDA device; there is no CPU fallback.")
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -43,12 +47,19 @@ def minimum_phase_decomposition(cross_spectral_matrix, tolerance=1e-8, max_itera
     out = torch.empty_like(c)
     iters = torch.zeros(nb, dtype=torch.int32, device=dev)
     flags = torch.zeros(nb, dtype=torch.int32, device=dev)
-    ws_bytes = lib.sc_wilson_workspace_bytes(nfft)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     tw = twiddles(nfft, torch.complex128, dev)
-    rc = lib.sc_wilson2(_lib.ptr(c), nb, nfft, float(tolerance), int(max_iterations), _lib.ptr(tw), _lib.ptr(out),
-                        _lib.ptr(iters), _lib.ptr(flags), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
-    _lib.check(rc, "sc_wilson2")
+    if n_sig == 2:
+        ws_bytes = lib.sc_wilson_workspace_bytes(nfft)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rc = lib.sc_wilson2(_lib.ptr(c), nb, nfft, float(tolerance), int(max_iterations), _lib.ptr(tw), _lib.ptr(out),
+                            _lib.ptr(iters), _lib.ptr(flags), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "sc_wilson2")
+    else:
+        ws_bytes = lib.sc_wilson_general_workspace_bytes(nb, nfft, n_sig)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rc = lib.sc_wilson(_lib.ptr(c), nb, nfft, nfft, 0, n_sig, float(tolerance), int(max_iterations), _lib.ptr(tw),
+                           _lib.ptr(out), _lib.ptr(iters), _lib.ptr(flags), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "sc_wilson")
     n_bad = int((flags & _lib.FLAG_NOT_CONVERGED).ne(0).sum())
     if n_bad:
         logger.warning(f"Maximum iterations reached. {nb - n_bad} of {nb} converged")

@@ -143,6 +143,16 @@ def main():
     wil["csm4"] = csm
     wil["g4"] = np.asarray(M.minimum_phase_decomposition(csm))
     np.savez_compressed(os.path.join(HERE, "wilson.npz"), **wil)
+    # ---- 6. MVAR family (full-matrix Wilson) -----------------------------------
+    mv = {}
+    c = C.Connectivity(coef, frequencies=m.frequencies, time=m.time)
+    mv["transfer_function"] = np.asarray(c._transfer_function)
+    mv["noise_covariance"] = np.asarray(c._noise_covariance)
+    mv["mvar_fourier_coefficients"] = np.asarray(c._MVAR_Fourier_coefficients)
+    for meth in ["directed_transfer_function", "directed_coherence", "partial_directed_coherence",
+                 "generalized_partial_directed_coherence", "direct_directed_transfer_function"]:
+        mv[meth] = np.asarray(getattr(c, meth)())
+    np.savez_compressed(os.path.join(HERE, "mvar.npz"), **mv)
     print("golden fixtures written to", HERE)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

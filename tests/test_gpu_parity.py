@@ -379,3 +379,76 @@ def test_csm_tensor_core_matches_simt_and_fp64(sc, n_sig, n_obs, n_bf):
     pw = np.sqrt(np.einsum("bii->bi", ref_np).real)
     norm = pw[:, :, None] * pw[:, None, :]
     assert (np.abs(tc_np - ref_np) / norm).max() < 5e-6
+
+
+# --------------------------------------------------------------------------- #
+# general S x S Wilson + MVAR family
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("s", [3, 4])
+def test_wilson_general_golden(sc, s):
+    g = golden("wilson.npz")
+    got, iters, flags = sc.minimum_phase_decomposition(g[f"csm{s}"], return_info=True)
+    assert_parity(got, g[f"g{s}"], 1e-9, f"wilson S={s}")
+    _, ref_it = O.wilson(g[f"csm{s}"], return_iterations=True)
+    assert np.array_equal(iters, ref_it) and not flags.any()
+
+
+def test_wilson_general_matches_2x2_kernel(sc):
+    g = golden("wilson.npz")
+    from spectral_connectivity_b200 import _lib
+    from spectral_connectivity_b200.transforms import twiddles
+    lib = _lib.load()
+    c = torch.from_numpy(g["csm2"]).cuda().to(torch.complex128).contiguous()
+    nb, nfft = c.shape[0], c.shape[1]
+    out = torch.empty_like(c)
+    it = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    fl = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    wsb = lib.sc_wilson_general_workspace_bytes(nb, nfft, 2)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    tw = twiddles(nfft, torch.complex128, c.device)
+    _lib.check(lib.sc_wilson(_lib.ptr(c), nb, nfft, nfft, 0, 2, 1e-8, 60, _lib.ptr(tw), _lib.ptr(out), _lib.ptr(it),
+                             _lib.ptr(fl), _lib.ptr(ws), wsb, _lib.stream_ptr()), "sc_wilson")
+    assert_parity(out.cpu().numpy(), g["g2"], 1e-9, "general kernel on 2x2")
+
+
+MVAR = ["directed_transfer_function", "directed_coherence", "partial_directed_coherence",
+        "generalized_partial_directed_coherence", "direct_directed_transfer_function"]
+
+
+def test_mvar_family_from_coefficients_golden(sc):
+    g, mv = golden("connectivity.npz"), golden("mvar.npz")
+    c = sc.Connectivity(g["coef"])           # two-sided path (user-supplied coefficients)
+    assert_parity(c._transfer_function, mv["transfer_function"], TOL, "H")
+    assert_parity(c._noise_covariance, mv["noise_covariance"], TOL, "Sigma")
+    assert_parity(c._MVAR_Fourier_coefficients, mv["mvar_fourier_coefficients"], TOL, "A")
+    for name in MVAR:
+        assert_parity(getattr(c, name)(), mv[name], 2e-5 if "direct_directed" in name else TOL, name)
+
+
+def test_mvar_family_from_multitaper_golden(sc):
+    g, mv = golden("connectivity.npz"), golden("mvar.npz")
+    fs, nw, dur = g["meta"]
+    m = sc.Multitaper(g["x"], sampling_frequency=fs, time_halfbandwidth_product=nw, time_window_duration=dur)
+    c = sc.Connectivity.from_multitaper(m)   # real-series path: half spectrum, hermitian Wilson
+    assert_parity(c._transfer_function, mv["transfer_function"], TOL, "H")
+    for name in MVAR:
+        assert_parity(getattr(c, name)(), mv[name], 2e-5 if "direct_directed" in name else TOL, name)
+    assert int(c.last_wilson_flags.sum()) == 0
+
+
+def test_mvar_ranges_larger_system(sc):
+    """DTF/PDC are in [0,1] and normalise to 1 over sources/targets (reference tests/test_metric_ranges.py)."""
+    fs = 500.0
+    x = O.synthetic_series(4000, 8, 12, fs, seed=21)
+    c = sc.Connectivity.from_multitaper(sc.Multitaper(x, fs, 3, time_window_duration=1.0))
+    dtf = c.directed_transfer_function()
+    pdc = c.partial_directed_coherence()
+    assert dtf.shape == (8, 251, 12, 12)
+    assert np.all((dtf >= 0) & (dtf <= 1 + 1e-6)) and np.all((pdc >= 0) & (pdc <= 1 + 1e-6))
+    assert np.allclose(dtf.sum(axis=-1), 1, atol=1e-5) and np.allclose(pdc.sum(axis=-2), 1, atol=1e-5)
+    coef = O.multitaper_fft(x.astype(np.float32).astype(np.float64), fs, O.dpss_tapers(500, 3, 5, fs), 500, 500, 500)
+    h, _ = O.mvar_transfer_function(O.expected_csm(coef, row_block=4))
+    assert_parity(dtf, O.directed_transfer_function(h), TOL, "DTF vs oracle S=12")
+    with pytest.raises(NotImplementedError):
+        big = sc.Connectivity(np.zeros((1, 2, 1, 8, 40), dtype=complex))
+        big.directed_transfer_function()

@@ -114,3 +114,20 @@ def test_csm_known_answer():
     coef[..., :] = [2 * np.exp(1j * np.pi / 2), 3 * np.exp(-1j * np.pi / 2)]
     assert np.allclose(O.cross_spectral_matrix(coef)[0, 0, 0, 0], [[4, -6], [-6, 9]])
     assert np.allclose(O.power(coef)[0, 0], [4, 9])
+
+
+def test_mvar_family():
+    g = golden("connectivity.npz")
+    mv = golden("mvar.npz")
+    csm = O.expected_csm(g["coef"])
+    h, sigma = O.mvar_transfer_function(csm)
+    assert_parity(h, mv["transfer_function"], 1e-8, "H")
+    assert_parity(sigma, mv["noise_covariance"], 1e-8, "Sigma")
+    a = O.mvar_fourier_coefficients(h)
+    assert_parity(a, mv["mvar_fourier_coefficients"], 1e-8, "A")
+    assert_parity(O.directed_transfer_function(h), mv["directed_transfer_function"], 1e-8, "DTF")
+    assert_parity(O.directed_coherence(h, sigma), mv["directed_coherence"], 1e-8, "DC")
+    assert_parity(O.partial_directed_coherence(a), mv["partial_directed_coherence"], 1e-8, "PDC")
+    assert_parity(O.generalized_partial_directed_coherence(a, sigma), mv["generalized_partial_directed_coherence"],
+                  1e-8, "gPDC")
+    assert_parity(O.direct_directed_transfer_function(h, a), mv["direct_directed_transfer_function"], 1e-8, "dDTF")
