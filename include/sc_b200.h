@@ -180,6 +180,22 @@ int sc_mvar_inverse(const void* h_c128, double lambda, int64_t BF, int S, void* 
 int sc_mvar_measure(int measure, const void* h_c128, const void* a_c128, const double* sigma, int64_t B, int F, int S,
                     double* scratch, float* out, void* stream);
 
+/* canonical_coherence(group_labels) -- connectivity.py:745-820, 1979-2032: squared canonical coherence between
+ * signal groups from the expected CSM (c64 [B][F][S][S]): per (b, f, group pair) two Cholesky factorisations, two
+ * triangular solves and the top eigenvalue of M M^H.  group_index int32 [S] lists the signals sorted by group,
+ * group_offsets int32 [n_groups+1] delimits them (both device); groups hold at most 64 signals.
+ * out f32 [B][F][n_groups][n_groups]; only off-diagonal entries are written (the caller pre-fills NaN, :797).
+ * out_flags int32 [B*F] or NULL: SC_FLAG_NOT_SPD when a group's block is not positive definite (fewer
+ * observations than signals). */
+int sc_canonical_coherence(const void* csm_c64, int64_t B, int F, int S, const int* group_index,
+                           const int* group_offsets, int n_groups, int max_group_size, float* out, int* out_flags,
+                           void* stream);
+
+/* global_coherence(max_rank=1) -- connectivity.py:822-895, 2245-2279: largest eigenvalue of each CSM
+ * (c64 [BF][S][S], S <= 64) = top singular value^2 / n_observations, and its unit eigenvector (c64 [BF][S],
+ * defined up to a phase like the reference's SVD output). */
+int sc_global_coherence(const void* csm_c64, int64_t BF, int S, float* out_value, void* out_vector_c64, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -480,6 +480,44 @@ def direct_directed_transfer_function(h, a):
 
 
 # --------------------------------------------------------------------------- #
+# SVD-based measures
+# --------------------------------------------------------------------------- #
+def _obs_matrix(coef):
+    """(W,T,K,F,S) -> (W,F,S,T*K) (connectivity.py:1953-1976)."""
+    w, t, k, f, s = coef.shape
+    return np.moveaxis(coef.reshape(w, t * k, f, s), 1, -1)
+
+
+def canonical_coherence(coef, group_labels):
+    """(W, Fnn, G, G) squared canonical coherence between signal groups, NaN diagonal, and the
+    sorted labels (connectivity.py:745-820, 1979-2032)."""
+    group_labels = np.asarray(group_labels)
+    labels = np.unique(group_labels)
+    nf = coef.shape[-2]
+    half = coef[..., : nf // 2 + 1, :]
+    whitened = []
+    for lab in labels:
+        u, _, vh = np.linalg.svd(_obs_matrix(half[..., group_labels == lab]), full_matrices=False)
+        whitened.append(u @ vh)
+    n_g = len(labels)
+    out = np.full(half.shape[:1] + (half.shape[-2], n_g, n_g), np.nan)
+    for a, b in combinations(range(n_g), 2):
+        cross = whitened[a] @ np.conj(np.swapaxes(whitened[b], -1, -2))
+        sv = np.linalg.svd(cross, compute_uv=False)[..., 0]
+        out[..., a, b] = out[..., b, a] = np.abs(sv) ** 2
+    return out, labels
+
+
+def global_coherence(coef):
+    """Largest eigenvalue of the per-(window, frequency) cross-spectral matrix = top singular value
+    squared / n_observations, over ALL Nfft bins, and its eigenvector (defined up to a phase)
+    (connectivity.py:822-895, 2245-2279 with max_rank = 1)."""
+    x = _obs_matrix(coef)
+    u, sv, _ = np.linalg.svd(x, full_matrices=False)
+    return sv[..., :1] ** 2 / x.shape[-1], u[..., :, :1]
+
+
+# --------------------------------------------------------------------------- #
 # deterministic synthetic workloads (BASELINE.md section 3, SURVEY.md section 8d)
 # --------------------------------------------------------------------------- #
 CONFIGS = {

@@ -175,11 +175,12 @@ class Connectivity:
         return host.numpy()
 
     # ---- streaming engine ----------------------------------------------------------
-    def _chunks(self, n_freq):
+    def _chunks(self, n_freq, expectation_type=None):
         """Yield (b0, b1, planar chunk [b1-b0][n_freq][2][R][S], R)."""
         lib = _lib.load()
+        expectation_type = expectation_type or self.expectation_type
         n_win, n_trials, n_tapers, nfft, n_sig = self._shape
-        time_kept = 0 not in EXPECTATION_AXES[self.expectation_type]
+        time_kept = 0 not in EXPECTATION_AXES[expectation_type]
         if time_kept:
             per_window = n_trials * n_tapers * n_freq * n_sig * 8
             wc = max(1, min(n_win, self._max_chunk_bytes // max(per_window, 1)))
@@ -187,7 +188,7 @@ class Connectivity:
             wc = n_win
         for w0 in range(0, n_win, wc):
             w1 = min(n_win, w0 + wc)
-            mapping, kept, nb, nr = expectation_map((w1 - w0, n_trials, n_tapers), self.expectation_type)
+            mapping, kept, nb, nr = expectation_map((w1 - w0, n_trials, n_tapers), expectation_type)
             xp = torch.empty((nb, n_freq, 2, nr, n_sig), dtype=torch.float32, device=self._device)
             if self._mt is not None:
                 self._mt._transform(xp, _lib.LAYOUT_PLANAR, n_freq, w0, w1 - w0, 0, mapping, nr)
@@ -634,11 +635,68 @@ class Connectivity:
         raise NotImplementedError(
             f"{name} is outside the current hot-path scope (SURVEY.md section 8f); see DESIGN.md")
 
+    def _trials_tapers_csm(self, n_freq):
+        """Expected CSM over trials x tapers per window (what the SVD-based measures are built on; they
+        merge trials and tapers whatever ``expectation_type`` says, connectivity.py:1953-1976)."""
+        lib = _lib.load()
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        scale = 1.0 / (n_trials * n_tapers)
+        csm = torch.empty((n_win, n_freq, n_sig, n_sig), dtype=torch.complex64, device=self._device)
+        st = _lib.stream_ptr()
+        for b0, b1, xp, nr in self._chunks(n_freq, "trials_tapers"):
+            _lib.check(lib.sc_csm(_lib.ptr(xp), b1 - b0, n_freq, nr, n_sig, scale, _lib.CSM_CROSS,
+                                  _lib.ptr(csm[b0:b1]), st), "sc_csm")
+            self._allreduce(csm[b0:b1])
+        return csm
+
     def canonical_coherence(self, group_labels):
-        self._next_round("canonical_coherence")
+        """Squared canonical coherence between signal groups, shape (n_windows, n_frequencies, n_groups,
+        n_groups) with NaN diagonal, and the sorted group labels (connectivity.py:745-820).  Computed from
+        the expected CSM (block whitening) instead of per-group SVDs of the coefficients; groups of up to
+        64 signals, each needing at least as many observations (trials x tapers) as signals."""
+        lib = _lib.load()
+        group_labels = np.asarray(group_labels)
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        if group_labels.shape != (n_sig,):
+            raise ValueError(f"group_labels must have one entry per signal ({n_sig}), got shape {group_labels.shape}")
+        labels = np.unique(group_labels)
+        n_groups = len(labels)
+        fnn = nfft // 2 + 1
+        out = torch.full((n_win, fnn, n_groups, n_groups), float("nan"), dtype=torch.float32, device=self._device)
+        if n_groups >= 2:
+            order = np.concatenate([np.flatnonzero(group_labels == lab) for lab in labels]).astype(np.int32)
+            sizes = np.array([(group_labels == lab).sum() for lab in labels])
+            if sizes.max() > 64:
+                raise NotImplementedError("canonical_coherence on the device handles groups of up to 64 signals")
+            offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+            gidx = torch.from_numpy(order).to(self._device)
+            goff = torch.from_numpy(offsets).to(self._device)
+            csm = self._trials_tapers_csm(fnn)
+            flags = torch.zeros(n_win * fnn, dtype=torch.int32, device=self._device)
+            _lib.check(lib.sc_canonical_coherence(_lib.ptr(csm), n_win, fnn, n_sig, _lib.ptr(gidx), _lib.ptr(goff),
+                                                  n_groups, int(sizes.max()), _lib.ptr(out), _lib.ptr(flags),
+                                                  _lib.stream_ptr()), "sc_canonical_coherence")
+            if int(flags.ne(0).sum()):
+                logger.warning("canonical_coherence: some group blocks of the cross-spectral matrix are not positive "
+                               "definite (fewer observations than signals in a group); those entries are NaN.")
+        return self._finish(out), labels
 
     def global_coherence(self, max_rank=1):
-        self._next_round("global_coherence")
+        """Largest eigenvalue of the cross-spectral matrix per (window, frequency) over ALL n_fft bins and
+        its eigenvector: shapes (n_windows, n_fft, 1) and (n_windows, n_fft, n_signals, 1)
+        (connectivity.py:822-895).  The eigenvector is defined up to a phase, as in the reference's SVD."""
+        if max_rank != 1:
+            raise NotImplementedError("global_coherence on the device returns the leading component only (max_rank=1)")
+        lib = _lib.load()
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        if n_sig > 64:
+            raise NotImplementedError("global_coherence on the device handles up to 64 signals")
+        csm = self._trials_tapers_csm(nfft)
+        val = torch.empty((n_win, nfft, 1), dtype=torch.float32, device=self._device)
+        vec = torch.empty((n_win, nfft, n_sig, 1), dtype=torch.complex64, device=self._device)
+        _lib.check(lib.sc_global_coherence(_lib.ptr(csm), n_win * nfft, n_sig, _lib.ptr(val), _lib.ptr(vec),
+                                           _lib.stream_ptr()), "sc_global_coherence")
+        return self._finish(val), self._finish(vec)
 
     def group_delay(self, *args, **kwargs):
         self._next_round("group_delay")

@@ -153,6 +153,22 @@ def main():
                  "generalized_partial_directed_coherence", "direct_directed_transfer_function"]:
         mv[meth] = np.asarray(getattr(c, meth)())
     np.savez_compressed(os.path.join(HERE, "mvar.npz"), **mv)
+
+    # ---- 7. SVD-based measures ---------------------------------------------------
+    sv = {}
+    x6 = series(9, 300, 5, 6, 100.0)
+    m6 = T.Multitaper(x6, sampling_frequency=100.0, time_halfbandwidth_product=3, time_window_duration=1.0)
+    c6 = C.Connectivity.from_multitaper(m6)
+    labels = np.array([2, 0, 0, 1, 2, 1])
+    cc, lab = c6.canonical_coherence(labels)
+    gc_, gv_ = c6.global_coherence(max_rank=5)   # max_rank >= n_signals - 1: dense SVD branch (:2258-2266)
+    sv["x"] = x6
+    sv["labels"] = labels
+    sv["canonical_coherence"] = np.asarray(cc)
+    sv["canonical_labels"] = np.asarray(lab)
+    sv["global_coherence"] = np.asarray(gc_)[..., :1]
+    sv["global_vectors"] = np.asarray(gv_)[..., :1]
+    np.savez_compressed(os.path.join(HERE, "svd_measures.npz"), **sv)
     print("golden fixtures written to", HERE)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -452,3 +452,36 @@ def test_mvar_ranges_larger_system(sc):
     with pytest.raises(NotImplementedError):
         big = sc.Connectivity(np.zeros((1, 2, 1, 8, 40), dtype=complex))
         big.directed_transfer_function()
+
+
+# --------------------------------------------------------------------------- #
+# SVD-based measures
+# --------------------------------------------------------------------------- #
+def test_canonical_and_global_coherence_golden(sc):
+    g = golden("svd_measures.npz")
+    m = sc.Multitaper(g["x"], sampling_frequency=100.0, time_halfbandwidth_product=3, time_window_duration=1.0)
+    c = sc.Connectivity.from_multitaper(m)
+    cc, labels = c.canonical_coherence(g["labels"])
+    assert np.array_equal(labels, g["canonical_labels"])
+    assert_parity(cc, g["canonical_coherence"], TOL, "canonical coherence")
+    val, vec = c.global_coherence()
+    assert val.shape == (3, 100, 1) and vec.shape == (3, 100, 6, 1)
+    assert_parity(val, g["global_coherence"], TOL, "global coherence")
+    overlap = np.abs(np.sum(np.conj(vec) * g["global_vectors"], axis=-2))
+    assert np.allclose(overlap, 1.0, atol=1e-4)
+
+
+def test_canonical_coherence_larger_groups_vs_oracle(sc):
+    fs = 500.0
+    x = O.synthetic_series(1500, 6, 40, fs, seed=31)
+    labels = np.arange(40) // 10        # 4 groups of 10 signals, 30 observations
+    labels[[3, 17]] = 3                 # ragged group sizes: 9, 9, 10, 12
+    c = sc.Connectivity.from_multitaper(sc.Multitaper(x, fs, 3, time_window_duration=1.0))
+    cc, lab = c.canonical_coherence(labels)
+    coef = O.multitaper_fft(x.astype(np.float32).astype(np.float64), fs, O.dpss_tapers(500, 3, 5, fs), 500, 500, 500)
+    ref, ref_lab = O.canonical_coherence(coef, labels)
+    assert np.array_equal(lab, ref_lab)
+    assert_parity(cc, ref, 2e-5, "canonical coherence, 4 ragged groups")
+    assert np.all((cc[~np.isnan(cc)] >= 0) & (cc[~np.isnan(cc)] <= 1 + 1e-5))
+    sym = np.swapaxes(cc, -1, -2)
+    assert np.array_equal(np.isnan(cc), np.isnan(sym)) and np.nanmax(np.abs(cc - sym)) == 0

@@ -131,3 +131,18 @@ def test_mvar_family():
     assert_parity(O.generalized_partial_directed_coherence(a, sigma), mv["generalized_partial_directed_coherence"],
                   1e-8, "gPDC")
     assert_parity(O.direct_directed_transfer_function(h, a), mv["direct_directed_transfer_function"], 1e-8, "dDTF")
+
+
+def test_svd_measures():
+    g = golden("svd_measures.npz")
+    fs = 100.0
+    taps = O.dpss_tapers(100, 3, 5, fs)
+    coef = O.multitaper_fft(g["x"], fs, taps, 100, 100, 100)
+    cc, lab = O.canonical_coherence(coef, g["labels"])
+    assert np.array_equal(lab, g["canonical_labels"])
+    assert_parity(cc, g["canonical_coherence"], 1e-8, "canonical coherence")
+    gc, gv = O.global_coherence(coef)
+    assert_parity(gc, g["global_coherence"], 1e-8, "global coherence")
+    # eigenvectors agree up to a unit-modulus factor
+    overlap = np.abs(np.sum(np.conj(gv) * g["global_vectors"], axis=-2))
+    assert np.allclose(overlap, 1.0, atol=1e-6)
