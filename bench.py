@@ -35,6 +35,9 @@ WORKLOADS = {
     "cfg1": dict(N=1000, T=4, S=8, fs=500.0, NW=2.0, duration=None),
 }
 MEASURES = ["coherence_magnitude", "pairwise_spectral_granger_prediction"]
+# the other BASELINE.json configs are parity-test cases; `--workload` can still time them
+WORKLOAD_MEASURES = {"cfg1": ["coherence_magnitude"], "cfg2": ["power", "coherency"],
+                     "cfg3": ["expectation_cross_spectral_matrix", "weighted_phase_lag_index"]}
 METRIC = "channel-pair-freqs/sec (CSM+coherence+Granger)"
 FP64_PEAK_NOMINAL_TFLOPS = 37.0  # B200 FP64 vector, nominal (not in MEASURED_PEAKS.json)
 
@@ -131,8 +134,8 @@ def workload_config(wl_name, wl, n_gpus):
     n, n_win, nfft, fnn = geometry(wl)
     return {"workload": f"BASELINE configs[{wl_name[3]}]{' (reduced windows)' if len(wl_name) > 4 else ''}: {wl['S']}-channel x {wl['T']}-trial x "
                         f"{wl['N'] / wl['fs']:.0f} s @ {wl['fs']:.0f} Hz, {int(2 * wl['NW'] - 1)} tapers, "
-                        f"{n_win} windows of {n} samples, nfft {nfft}; coherence_magnitude + "
-                        "pairwise_spectral_granger_prediction (Wilson tol 1e-8, <=60 it)",
+                        f"{n_win} windows of {n} samples, nfft {nfft}; " + " + ".join(WORKLOAD_MEASURES.get(wl_name, MEASURES)) +
+                        (" (Wilson tol 1e-8, <=60 it)" if wl_name not in WORKLOAD_MEASURES else ""),
             "per_gpu_recording": [wl["N"], wl["T"], wl["S"]], "pair_freqs_per_gpu_step": pair_freqs(wl),
             "parallelism": f"window-sharded x{n_gpus} (one recording shard per GPU, no collective)",
             "l2": "inputs (3.9 GB) and every intermediate exceed the 126 MB L2; no explicit flush"}
@@ -222,10 +225,13 @@ def run_gpu(args, wl_name, wl):
     kw = dict(sampling_frequency=wl["fs"], time_halfbandwidth_product=wl["NW"],
               time_window_duration=wl["duration"])
 
+    measures = WORKLOAD_MEASURES.get(wl_name, MEASURES)
+    has_granger = "pairwise_spectral_granger_prediction" in measures
+
     def step_device():
         m = sc.Multitaper(x_dev, **kw)
         c = sc.Connectivity.from_multitaper(m, output="torch")
-        out = c.compute(MEASURES)
+        out = c.compute(measures)
         return c, out
 
     def barrier():
@@ -265,17 +271,20 @@ def run_gpu(args, wl_name, wl):
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = units * world / (ms_step * 1e-3)
-    iters = c.last_granger_iterations.to(torch.float64)
-    mean_iters = float(iters.mean())
-    n_problems = iters.numel()
-    flags = int(c.last_granger_flags.ne(0).sum())
-    gc = out["pairwise_spectral_granger_prediction"]
-    coh = out["coherence_magnitude"]
-    sanity = {"granger_nan_frac": float(torch.isnan(gc).float().mean()),
-              "granger_max": float(torch.nan_to_num(gc, nan=0.0).max()),
-              "coherence_mean_offdiag": float(torch.nanmean(coh)), "wilson_flagged": flags,
-              "wilson_mean_iters": mean_iters}
-    del out, gc, coh
+    mean_iters, n_problems, sanity = 0.0, 0, {}
+    if has_granger:
+        iters = c.last_granger_iterations.to(torch.float64)
+        mean_iters = float(iters.mean())
+        n_problems = iters.numel()
+        flags = int(c.last_granger_flags.ne(0).sum())
+        gc = out["pairwise_spectral_granger_prediction"]
+        coh = out["coherence_magnitude"]
+        sanity = {"granger_nan_frac": float(torch.isnan(gc).float().mean()),
+                  "granger_max": float(torch.nan_to_num(gc, nan=0.0).max()),
+                  "coherence_mean_offdiag": float(torch.nanmean(coh)), "wilson_flagged": flags,
+                  "wilson_mean_iters": mean_iters}
+        del gc, coh
+    del out
 
     # ---- end to end through the public API with host buffers -----------------------------
     x_host = torch.empty(x_dev.shape, dtype=torch.float32, pin_memory=True)
@@ -286,7 +295,7 @@ def run_gpu(args, wl_name, wl):
     def step_e2e():
         m = sc.Multitaper(x_np, **kw)                      # H2D from pinned host memory
         cc = sc.Connectivity.from_multitaper(m)            # output="numpy": D2H of every result
-        return cc.compute(MEASURES)
+        return cc.compute(measures)
 
     e2e_steps = max(1, min(args.steps, 3))
     res = step_e2e()
@@ -374,7 +383,7 @@ def run_gpu(args, wl_name, wl):
                 "h2d_bytes_per_step": int(x_np.nbytes), "d2h_bytes_per_step": d2h, "steps": e2e_steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stages": stage_rows, "sanity": sanity,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and has_granger:
         cb = cpu_sample(wl)
         line["cpu_baseline"] = {"value": units / cb["est_step_seconds"], "unit": "pair-freqs/s",
                                 "cores": cpu_threads(), "kind": "port", "sample": cb["sample"],
