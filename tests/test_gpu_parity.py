@@ -485,3 +485,18 @@ def test_canonical_coherence_larger_groups_vs_oracle(sc):
     assert np.all((cc[~np.isnan(cc)] >= 0) & (cc[~np.isnan(cc)] <= 1 + 1e-5))
     sym = np.swapaxes(cc, -1, -2)
     assert np.array_equal(np.isnan(cc), np.isnan(sym)) and np.nanmax(np.abs(cc - sym)) == 0
+
+
+def test_trial_sharded_allreduce_two_gpus(sc):
+    """Partitioning B: ranks hold disjoint trials of the same windows; partial sums are
+    all-reduced over NCCL before the epilogues / Wilson.  Needs two GPUs (skipped otherwise)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dist_trial_shard_worker.py")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", worker],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
