@@ -157,33 +157,33 @@ __global__ void epilogue_kernel(int measure, const float* __restrict__ in0, cons
                                 long long BF, long long S, double nobs, float* __restrict__ out) {
     const long long total = BF * S * S;
     const float qnan = __int_as_float(0x7fc00000);
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const long long j = idx % S;
-        const long long i = (idx / S) % S;
-        const long long bf = idx / (S * S);
+    // one matrix row (bf, i) per block iteration, threads over j: no per-element 64-bit divisions
+    for (long long row = blockIdx.x; row < BF * S; row += gridDim.x) {
+      const long long bf = row / S;
+      const long long i = row - bf * S;
+      for (long long j = threadIdx.x; j < S; j += blockDim.x) {
+        const long long idx = row * S + j;
         switch (measure) {
             case SC_M_COHERENCY:
             case SC_M_COHERENCE_MAG:
             case SC_M_COHERENCE_PHASE:
             case SC_M_IMAG_COHERENCE: {
+                // fp32 throughout: inputs are fp32 and the normalisation is well conditioned (1e-7 relative);
+                // sqrt(p_i) * sqrt(p_j) cannot under/overflow where p_i * p_j could
                 const float2 c = reinterpret_cast<const float2*>(in0)[idx];
-                const double pi_ = in1[bf * S + i], pj = in1[bf * S + j];
-                double norm = sqrt(pi_ * pj);
-                norm = norm > kEps64 ? norm : kEps64;  // connectivity.py:649-652
-                const double re = c.x / norm, im = c.y / norm;
+                float norm = sqrtf(in1[bf * S + i]) * sqrtf(in1[bf * S + j]);
+                norm = fmaxf(norm, (float)kEps64);  // connectivity.py:649-652
+                const float inv = 1.0f / norm;
+                const float re = c.x * inv, im = c.y * inv;
                 if (measure == SC_M_COHERENCY) {
-                    reinterpret_cast<float2*>(out)[idx] = i == j ? make_float2(qnan, qnan) : make_float2((float)re, (float)im);
+                    reinterpret_cast<float2*>(out)[idx] = i == j ? make_float2(qnan, qnan) : make_float2(re, im);
                 } else if (measure == SC_M_COHERENCE_MAG) {
-                    double m = re * re + im * im;
-                    m = m < 0.0 ? 0.0 : (m > 1.0 ? 1.0 : m);
-                    out[idx] = i == j ? qnan : (float)m;
+                    const float m = fminf(fmaxf(fmaf(re, re, im * im), 0.f), 1.f);
+                    out[idx] = i == j ? qnan : m;
                 } else if (measure == SC_M_COHERENCE_PHASE) {
-                    out[idx] = i == j ? qnan : (float)atan2(im, re);
+                    out[idx] = i == j ? qnan : atan2f(im, re);
                 } else {
-                    double m = fabs(im);
-                    m = m > 1.0 ? 1.0 : m;
-                    out[idx] = (float)m;
+                    out[idx] = fminf(fabsf(im), 1.f);
                 }
                 break;
             }
@@ -220,6 +220,7 @@ __global__ void epilogue_kernel(int measure, const float* __restrict__ in0, cons
             }
             default: break;
         }
+      }
     }
 }
 
@@ -278,7 +279,10 @@ extern "C" int sc_pairwise_epilogue(int measure, const void* in0, const float* i
     SC_CHECK_ARG(measure >= SC_M_COHERENCY && measure <= SC_M_DWPLI2, "sc_pairwise_epilogue: unknown measure %d", measure);
     SC_CHECK_ARG(measure > SC_M_IMAG_COHERENCE || in1, "sc_pairwise_epilogue: measure %d needs the power array", measure);
     SC_CHECK_ARG(B > 0 && F > 0 && S > 0, "sc_pairwise_epilogue: non-positive size");
-    epilogue_kernel<<<grid_for(B * F * S * S, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    const long long rows = B * F * S;
+    const int threads = S >= 256 ? 256 : (S >= 128 ? 128 : (S >= 64 ? 64 : 32));
+    const long long cap = (long long)sc_num_sms() * 64;
+    epilogue_kernel<<<(unsigned)(rows < cap ? rows : cap), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         measure, reinterpret_cast<const float*>(in0), in1, B * F, S, n_observations, reinterpret_cast<float*>(out));
     SC_LAUNCH_OK();
     return SC_OK;

@@ -500,3 +500,23 @@ def test_trial_sharded_allreduce_two_gpus(sc):
                           "--master-addr", "127.0.0.1", "--master-port", "29533", worker],
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n", [64, 101, 120, 250, 486, 1024, 2000])
+def test_granger_fft_lengths(sc, n):
+    """Pairwise Granger for FFT lengths that exercise every plan: compile-time (120), runtime radices
+    10/8/5/4/3/2, a prime length (101, O(p^2) stage) and 1..4 frequency bins per thread."""
+    fs = float(n)
+    x = O.synthetic_series(2 * n, 5, 3, fs, seed=n)
+    x += 0.3 * np.random.default_rng(n).standard_normal(x.shape)  # keep the spectra well conditioned
+    m = sc.Multitaper(x, sampling_frequency=fs, time_halfbandwidth_product=2, time_window_duration=1.0, n_fft_samples=n)
+    c = sc.Connectivity.from_multitaper(m)
+    got = c.pairwise_spectral_granger_prediction()
+    taps = O.dpss_tapers(n, 2, 3, fs)
+    coef = O.multitaper_fft(x.astype(np.float32).astype(np.float64), fs, taps, n, n, n)
+    ref, its = O.pairwise_granger(O.expected_csm(coef), O.power(coef), return_iterations=True)
+    assert_parity(got, ref, TOL, f"granger nfft={n}")
+    assert np.abs(c.last_granger_iterations.cpu().numpy() - np.array(its)).max() <= 1
+    # user-supplied (two-sided) coefficients take the general kernel
+    c2 = sc.Connectivity(coef)
+    assert_parity(c2.pairwise_spectral_granger_prediction(), ref, TOL, f"granger two-sided nfft={n}")
