@@ -378,6 +378,8 @@ class Connectivity:
                 logger.warning(f"Computing the initial conditions using the Cholesky failed for {n_spd} "
                                "(pair, window) problems; their Granger values are NaN.")
 
+        if self._mt is not None:
+            self._mt._check_finite_deferred()
         result = {}
         if copy_stream is not None:
             copy_stream.synchronize()

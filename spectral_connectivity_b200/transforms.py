@@ -128,10 +128,19 @@ class Multitaper:
         if not ts.is_floating_point():
             ts = ts.to(torch.float64)
         # host -> device copy (transforms.py:590 `xp.asarray`), then float32 on the device
-        self.time_series = ts.to(dev, non_blocking=True).to(torch.float32).contiguous()
-        if not bool(torch.isfinite(self.time_series).all()):
-            warnings.warn("Input time_series contains NaN or infinite values. This will produce "
-                          "invalid spectral estimates.", UserWarning, stacklevel=2)
+        self._h2d_events = None
+        self._finite_flag = None
+        self._host_src = None
+        if dev.type == "cuda" and not ts.is_cuda and ts.numel() * ts.element_size() >= self._ASYNC_H2D_BYTES:
+            # Large host arrays stream to the device in slabs of the time axis on a side stream; the
+            # transform of a window chunk only waits for the slabs it reads, so the copy overlaps the
+            # compute.  The NaN/Inf scan (transforms.py:754-774) runs on the device behind each slab and its
+            # warning is raised at the first synchronisation point (fft() / Connectivity.compute()).
+            self._stream_to_device(ts, dev)
+        else:
+            self.time_series = ts.to(dev, non_blocking=True).to(torch.float32).contiguous()
+            if not bool(torch.isfinite(self.time_series).all()):
+                warnings.warn(self._NONFINITE_MSG, UserWarning, stacklevel=2)
 
         self.sampling_frequency = sampling_frequency
         self.time_halfbandwidth_product = time_halfbandwidth_product
@@ -147,6 +156,54 @@ class Multitaper:
         self._n_samples_per_time_step = n_time_samples_per_step
         self._tapers_dev = None
         self._tw = {}
+
+    _ASYNC_H2D_BYTES = 256 << 20
+    _NONFINITE_MSG = ("Input time_series contains NaN or infinite values. This will produce "
+                      "invalid spectral estimates.")
+
+    def _stream_to_device(self, ts, dev, n_slabs=16):
+        ts = ts.contiguous()
+        self._host_src = ts  # keep the host buffer alive until the copies have run
+        n_rows = ts.shape[0]
+        self.time_series = torch.empty(tuple(ts.shape), dtype=torch.float32, device=dev)
+        self._finite_flag = torch.ones((), dtype=torch.bool, device=dev)
+        self._h2d_events = []
+        copy_stream = torch.cuda.Stream(device=dev)
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))
+        rows = max(1, -(-n_rows // n_slabs))
+        with torch.cuda.stream(copy_stream):
+            for r0 in range(0, n_rows, rows):
+                r1 = min(n_rows, r0 + rows)
+                dst = self.time_series[r0:r1]
+                if ts.dtype == torch.float32:
+                    dst.copy_(ts[r0:r1], non_blocking=True)
+                else:
+                    dst.copy_(ts[r0:r1].to(dev, non_blocking=True))
+                self._finite_flag &= torch.isfinite(dst).all()
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                self._h2d_events.append((r1, ev))
+        self.time_series.record_stream(copy_stream)
+
+    def _wait_rows(self, row_end):
+        """Make the current stream wait for the host->device slabs covering rows [0, row_end)."""
+        if not self._h2d_events:
+            return
+        cur = torch.cuda.current_stream(self.time_series.device)
+        for r1, ev in self._h2d_events:
+            cur.wait_event(ev)
+            if r1 >= row_end:
+                break
+
+    def _check_finite_deferred(self):
+        """Raise the deferred non-finite warning of the streamed copy (synchronises once)."""
+        if self._finite_flag is not None:
+            flag, self._finite_flag = self._finite_flag, None
+            self._wait_rows(self.time_series.shape[0])
+            if not bool(flag):
+                warnings.warn(self._NONFINITE_MSG, UserWarning, stacklevel=3)
+            self._h2d_events = None
+            self._host_src = None
 
     def __repr__(self):
         return ("Multitaper("
@@ -277,6 +334,7 @@ class Multitaper:
         ws_bytes = lib.sc_mt_fft_workspace_bytes(n, nfft)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device) if ws_bytes else None
         tw = self._twiddle()
+        self._wait_rows((w0 + n_win - 1) * step + n)
         with _lib.timed("mt_fft"):
             rc = lib.sc_mt_fft(_lib.ptr(self.time_series), n_samples, n_trials, n_signals, _lib.ptr(taps), n,
                                taps.shape[0], step, w0, n_win, w_out0, nfft, _lib.DETREND[self.detrend_type],
@@ -296,4 +354,5 @@ class Multitaper:
         out = torch.empty(shape, dtype=torch.complex64, device=_device())
         if out.numel():
             self._transform(out, _lib.LAYOUT_REFERENCE, self.n_fft_samples, 0, n_win)
+        self._check_finite_deferred()
         return out

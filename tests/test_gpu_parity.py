@@ -520,3 +520,24 @@ def test_granger_fft_lengths(sc, n):
     # user-supplied (two-sided) coefficients take the general kernel
     c2 = sc.Connectivity(coef)
     assert_parity(c2.pairwise_spectral_granger_prediction(), ref, TOL, f"granger two-sided nfft={n}")
+
+
+def test_streamed_host_to_device_copy(sc, monkeypatch):
+    """Large host inputs are copied in slabs on a side stream; results and the (deferred) NaN warning match."""
+    fs = 500.0
+    x = O.synthetic_series(3000, 3, 5, fs, seed=77)
+    kw = dict(sampling_frequency=fs, time_halfbandwidth_product=2, time_window_duration=0.5)
+    ref = sc.Connectivity.from_multitaper(sc.Multitaper(x, **kw)).compute(["coherence_magnitude", "power"])
+    monkeypatch.setattr(sc.Multitaper, "_ASYNC_H2D_BYTES", 1)
+    for arr in (x, x.astype(np.float32), torch.from_numpy(x.astype(np.float32)).pin_memory()):
+        m = sc.Multitaper(arr, **kw)
+        assert m._h2d_events is not None
+        got = sc.Connectivity.from_multitaper(m).compute(["coherence_magnitude", "power"])
+        for k in ref:
+            assert np.array_equal(np.isnan(got[k]), np.isnan(ref[k])) and np.nanmax(np.abs(got[k] - ref[k])) == 0
+        assert_parity(sc.Multitaper(arr, **kw).fft().cpu().numpy(), sc.Multitaper(x, **kw).fft().cpu().numpy(), 1e-7, "fft")
+    bad = x.copy()
+    bad[100, 1, 2] = np.nan
+    m = sc.Multitaper(bad, **kw)
+    with pytest.warns(UserWarning, match="NaN"):
+        m.fft()
