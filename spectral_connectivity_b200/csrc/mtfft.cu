@@ -86,11 +86,25 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
         // ---- load slab + detrend statistics --------------------------------
         double sum = 0.0, sumu = 0.0;
         const double ubar = (n + 1.0) / (2.0 * n);
-        for (int j = jr; j < n; j += JSTEP) {
-            const float v = s_ok ? __ldg(xw + (long long)j * row + sl) : 0.f;
-            if (!WS) tile[j * TS + sl] = v;
-            sum += v;
-            sumu += ((j + 1.0) / n - ubar) * v;
+        // 8 independent loads in flight per thread before any dependent use (the slab load is the
+        // exposed DRAM latency of the kernel)
+        constexpr int LD = 8;
+        for (int j0 = jr; j0 < n; j0 += LD * JSTEP) {
+            float v[LD];
+#pragma unroll
+            for (int u = 0; u < LD; ++u) {
+                const int j = j0 + u * JSTEP;
+                v[u] = (s_ok && j < n) ? __ldg(xw + (long long)j * row + sl) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < LD; ++u) {
+                const int j = j0 + u * JSTEP;
+                if (j < n) {
+                    if (!WS) tile[j * TS + sl] = v[u];
+                    sum += v[u];
+                    if (p.detrend == SC_DETREND_LINEAR) sumu += ((j + 1.0) / n - ubar) * v[u];
+                }
+            }
         }
         if (p.detrend != SC_DETREND_NONE) {
             red[0][threadIdx.x] = sum;

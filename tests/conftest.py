@@ -14,6 +14,14 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the C-ABI library is a build artefact (git-ignored): build it once if the tree is fresh
+    lib = os.path.join(ROOT, "spectral_connectivity_b200", "libsc_b200.so")
+    if not os.path.exists(lib):
+        import shutil
+        import subprocess
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "spectral_connectivity_b200", "csrc"), "-j8"],
+                           check=False, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def golden(name):
