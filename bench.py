@@ -356,12 +356,24 @@ def run_gpu(args, wl_name, wl):
                            unit="TFLOP/s")
             row["frac"] = row["achieved"] / row["peak"]
         stage_rows[name] = row
+    # DRAM traffic per launch from the committed ncu capture (scaled to this run's windows per launch)
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if wl_name == "cfg4":
+            for name, row in stage_rows.items():
+                if name in tj["dram_bytes_per_launch"]:
+                    per_window = tj["dram_bytes_per_launch"][name] / tj["windows_in_captured_launch"]
+                    row["traffic"] = per_window * n_win / max(row["launches_per_step"], 1)
+                    traffic[name] = row["traffic"]
+    except Exception:
+        pass
     dom = max(stage_rows, key=lambda k_: stage_rows[k_]["ms_per_step"]) if stage_rows else None
     roof = None
     if dom:
         r = stage_rows[dom]
         roof = {"kernel": dom, "bound": r.get("bound"), "achieved": r.get("achieved"), "peak": r.get("peak"),
-                "unit": r.get("unit"), "frac": r.get("frac"), "traffic": None,
+                "unit": r.get("unit"), "frac": r.get("frac"), "traffic": traffic.get(dom),
                 "peak_source": ("nominal B200 FP64 vector peak (not in MEASURED_PEAKS.json)" if r.get("bound") == "fp64"
                                 else f"{peak_src} HBM copy bandwidth"),
                 "ms_per_launch": r["ms_per_step"] / max(r["launches_per_step"], 1),
