@@ -120,7 +120,9 @@ __device__ bool cta_cholesky(cd* A, int n) {
         }
         __syncthreads();
     }
-    return bad_sh == 0;
+    const bool ok = bad_sh == 0;
+    __syncthreads();  // the next call resets bad_sh
+    return ok;
 }
 
 struct CanonParams {
