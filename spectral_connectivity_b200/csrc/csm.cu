@@ -172,18 +172,20 @@ __global__ void epilogue_kernel(int measure, const float* __restrict__ in0, cons
                 // sqrt(p_i) * sqrt(p_j) cannot under/overflow where p_i * p_j could
                 const float2 c = reinterpret_cast<const float2*>(in0)[idx];
                 float norm = sqrtf(in1[bf * S + i]) * sqrtf(in1[bf * S + j]);
-                norm = fmaxf(norm, (float)kEps64);  // connectivity.py:649-652
+                norm = norm < (float)kEps64 ? (float)kEps64 : norm;  // connectivity.py:649-652; NaN propagates like np.maximum
                 const float inv = 1.0f / norm;
                 const float re = c.x * inv, im = c.y * inv;
                 if (measure == SC_M_COHERENCY) {
                     reinterpret_cast<float2*>(out)[idx] = i == j ? make_float2(qnan, qnan) : make_float2(re, im);
                 } else if (measure == SC_M_COHERENCE_MAG) {
-                    const float m = fminf(fmaxf(fmaf(re, re, im * im), 0.f), 1.f);
+                    float m = fmaf(re, re, im * im);
+                    m = m < 0.f ? 0.f : (m > 1.f ? 1.f : m);  // np.clip semantics: NaN stays NaN
                     out[idx] = i == j ? qnan : m;
                 } else if (measure == SC_M_COHERENCE_PHASE) {
                     out[idx] = i == j ? qnan : atan2f(im, re);
                 } else {
-                    out[idx] = fminf(fabsf(im), 1.f);
+                    const float a = fabsf(im);
+                    out[idx] = a > 1.f ? 1.f : a;
                 }
                 break;
             }

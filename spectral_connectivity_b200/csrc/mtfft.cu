@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
         // 8 independent loads in flight per thread before any dependent use (the slab load is the
         // exposed DRAM latency of the kernel)
         constexpr int LD = 8;
+        int bad = 0;
         for (int j0 = jr; j0 < n; j0 += LD * JSTEP) {
             float v[LD];
 #pragma unroll
@@ -101,11 +102,16 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
                 const int j = j0 + u * JSTEP;
                 if (j < n) {
                     if (!WS) tile[j * TS + sl] = v[u];
+                    bad |= !isfinite(v[u]);
                     sum += v[u];
                     if (p.detrend == SC_DETREND_LINEAR) sumu += ((j + 1.0) / n - ubar) * v[u];
                 }
             }
         }
+        // A NaN/Inf would leak from one series into the one it shares a packed FFT with; such slabs
+        // (the reference only warns about them, transforms.py:754-774) take the unpacked path below,
+        // one series per complex FFT, so that exactly the affected channels come out non-finite.
+        const int unpack = __syncthreads_or(bad);
         if (p.detrend != SC_DETREND_NONE) {
             red[0][threadIdx.x] = sum;
             red[1][threadIdx.x] = sumu;
@@ -137,19 +143,28 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
 
         for (int k = 0; k < p.K; ++k) {
             const float* h = p.tapers + (size_t)k * n;
+          for (int half = 0; half < (unpack ? 2 : 1); ++half) {
             // ---- taper product, two real series per complex sequence --------
-            if (WS) {
+            if (WS || unpack) {
                 for (int idx = threadIdx.x; idx < NP * nfft; idx += kThreads) {
                     const int pp = idx % NP;
                     const int j = idx / NP;
                     cx<float> z = cmake<float>(0.f, 0.f);
                     if (j < ncopy) {
                         const float hv = __ldg(h + j);
-                        const float u = (j + 1.0f) / n;
-                        float v0 = (s0 + 2 * pp < p.S) ? __ldg(xw + (long long)j * row + 2 * pp) : 0.f;
-                        float v1 = (s0 + 2 * pp + 1 < p.S) ? __ldg(xw + (long long)j * row + 2 * pp + 1) : 0.f;
-                        v0 -= trend_a[2 * pp] * u + trend_b[2 * pp];
-                        v1 -= trend_a[2 * pp + 1] * u + trend_b[2 * pp + 1];
+                        const int sa = unpack ? half * NP + pp : 2 * pp;  // first (or only) series of this sequence
+                        float v0, v1 = 0.f;
+                        if (WS) {
+                            const float u = (j + 1.0f) / n;
+                            v0 = (s0 + sa < p.S) ? __ldg(xw + (long long)j * row + sa) : 0.f;
+                            v0 -= trend_a[sa] * u + trend_b[sa];
+                            if (!unpack) {
+                                v1 = (s0 + sa + 1 < p.S) ? __ldg(xw + (long long)j * row + sa + 1) : 0.f;
+                                v1 -= trend_a[sa + 1] * u + trend_b[sa + 1];
+                            }
+                        } else {
+                            v0 = tile[j * TS + sa];
+                        }
                         z = cmake<float>(v0 * hv, v1 * hv);
                     }
                     bufA[(size_t)pp * nfft + j] = z;
@@ -174,8 +189,31 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
             else
                 res = sc_cta_fft<float>(bufA, bufB, NP, nfft, p.plan, tw, false);
 
-            // ---- unpack the two real spectra and store -----------------------
             const long long wo = p.w_out0 + wl;
+            if (unpack) {
+                // ---- one series per sequence: X_s(f) = Z(f) --------------------------
+                const long long plane = p.R * p.S;
+                const long long b = wo * p.map.bw + t * p.map.bt + k * p.map.bk;
+                const long long r = wo * p.map.rw + t * p.map.rt + k * p.map.rk;
+                for (int idx = threadIdx.x; idx < p.nfo * NP; idx += kThreads) {
+                    const int pp = idx % NP;
+                    const int f = idx / NP;
+                    const int sgl = half * NP + pp;
+                    if (s0 + sgl >= p.S) continue;
+                    const cx<float> z = res[(size_t)pp * nfft + f];
+                    if (p.layout == SC_LAYOUT_PLANAR) {
+                        float* out = reinterpret_cast<float*>(p.out);
+                        out[((b * p.nfo + f) * 2 + 0) * plane + r * p.S + s0 + sgl] = p.scale * z.x;
+                        out[((b * p.nfo + f) * 2 + 1) * plane + r * p.S + s0 + sgl] = p.scale * z.y;
+                    } else {
+                        float2* out = reinterpret_cast<float2*>(p.out);
+                        out[((((wo * p.T + t) * p.K + k) * p.nfo) + f) * p.S + s0 + sgl] = make_float2(p.scale * z.x, p.scale * z.y);
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
+            // ---- unpack the two real spectra and store -----------------------
             if (p.layout == SC_LAYOUT_PLANAR) {
                 const long long b = wo * p.map.bw + t * p.map.bt + k * p.map.bk;
                 const long long r = wo * p.map.rw + t * p.map.rt + k * p.map.rk;
@@ -229,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
                 }
             }
             __syncthreads();
+          }
         }
     }
 }

@@ -541,3 +541,27 @@ def test_streamed_host_to_device_copy(sc, monkeypatch):
     m = sc.Multitaper(bad, **kw)
     with pytest.warns(UserWarning, match="NaN"):
         m.fft()
+
+
+def test_nan_in_one_channel_stays_in_that_channel(sc):
+    """A non-finite sample invalidates exactly the channels the reference invalidates (the packed real FFT
+    would otherwise leak it into the neighbouring channel)."""
+    fs = 200.0
+    x = O.synthetic_series(800, 2, 6, fs, seed=3)
+    x[250, 1, 2] = np.nan          # window 1, trial 1, channel 2
+    x[650, 0, 5] = np.inf          # window 3, trial 0, channel 5
+    kw = dict(sampling_frequency=fs, time_halfbandwidth_product=2, time_window_duration=1.0)
+    with pytest.warns(UserWarning, match="NaN"):
+        m = sc.Multitaper(x, **kw)
+    got = m.fft().cpu().numpy()
+    with np.errstate(invalid="ignore"):
+        ref = O.multitaper_fft(x, fs, O.dpss_tapers(200, 2, 3, fs), 200, 200, 200)
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    ok = np.isfinite(ref)
+    assert np.abs(got[ok] - ref[ok]).max() / np.abs(ref[ok]).max() < TOL
+    with pytest.warns(UserWarning):
+        c = sc.Connectivity.from_multitaper(sc.Multitaper(x, **kw))
+    coh = c.coherence_magnitude()
+    with np.errstate(invalid="ignore"):
+        ref_coh = O.coherence_magnitude(ref)
+    assert np.array_equal(np.isnan(coh), np.isnan(ref_coh))
