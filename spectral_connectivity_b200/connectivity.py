@@ -77,6 +77,12 @@ class Connectivity:
     def __init__(self, fourier_coefficients, expectation_type="trials_tapers", frequencies=None,
                  time=None, blocks=None, dtype=np.complex128, *, output="numpy",
                  max_chunk_bytes=4 << 30, reduce_group=None, _multitaper=None):
+        src = getattr(fourier_coefficients, "_sc_source", None)
+        if (_multitaper is None and src is not None and isinstance(fourier_coefficients, torch.Tensor)
+                and fourier_coefficients._version == src[1]):
+            # unmodified output of Multitaper.fft(): same as from_multitaper (connectivity.py:366-400)
+            _multitaper = src[0]
+            self._coef_given = fourier_coefficients
         self._mt = _multitaper
         if _multitaper is None:
             if fourier_coefficients.ndim != 5:
@@ -106,10 +112,10 @@ class Connectivity:
                               "series, the windowing parameters and any preprocessing.", UserWarning,
                               stacklevel=2)
             self._shape = tuple(self._coef.shape)
-            self._hermitian = False
+            self._hermitian = self._is_conjugate_symmetric(self._coef)
         else:
             m = _multitaper
-            self._coef = None
+            self._coef = getattr(self, "_coef_given", None)
             self._shape = (m.n_time_windows, m.n_trials, m.n_tapers_effective, m.n_fft_samples, m.n_signals)
             self._hermitian = True  # real time series: X(-f) = conj X(f)
         self.expectation_type = expectation_type
@@ -122,6 +128,21 @@ class Connectivity:
         self.time = time if not isinstance(time, torch.Tensor) else time.cpu().numpy()
         self.last_granger_iterations = None
         self.last_granger_flags = None
+
+    @staticmethod
+    def _is_conjugate_symmetric(coef, rtol=1e-6):
+        """True when X(-f) = conj X(f) along the frequency axis (coefficients of real time series): then the
+        non-negative bins carry everything and the half-spectrum Wilson/Granger kernels apply."""
+        nfft = coef.shape[3]
+        if nfft < 2 or coef.numel() == 0:
+            return False
+        scale = float(coef.abs().max())
+        if not np.isfinite(scale) or scale == 0.0:
+            return False
+        if float(coef[:, :, :, 0].imag.abs().max()) > rtol * scale:
+            return False
+        mirrored = torch.flip(coef[:, :, :, 1:], dims=(3,)).conj()
+        return float((coef[:, :, :, 1:] - mirrored).abs().max()) <= rtol * scale
 
     @classmethod
     def from_multitaper(cls, multitaper_instance, expectation_type="trials_tapers", blocks=None,

@@ -355,4 +355,7 @@ class Multitaper:
         if out.numel():
             self._transform(out, _lib.LAYOUT_REFERENCE, self.n_fft_samples, 0, n_win)
         self._check_finite_deferred()
+        # Tag the result so that the reference's two-step idiom ``Connectivity(fourier_coefficients=m.fft(), ...)``
+        # can take the fused real-series path (half spectrum, no re-layout) as long as the tensor is unmodified.
+        out._sc_source = (self, out._version)
         return out

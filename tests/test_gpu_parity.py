@@ -565,3 +565,47 @@ def test_nan_in_one_channel_stays_in_that_channel(sc):
     with np.errstate(invalid="ignore"):
         ref_coh = O.coherence_magnitude(ref)
     assert np.array_equal(np.isnan(coh), np.isnan(ref_coh))
+
+
+def test_two_step_idiom_uses_fused_path(sc):
+    """``Connectivity(fourier_coefficients=m.fft(), ...)`` -- the reference README idiom -- must give the same
+    results as from_multitaper; unmodified fft() output takes the fused path, real-series coefficients from
+    anywhere else are recognised as conjugate symmetric, anything else takes the general two-sided path."""
+    fs = 500.0
+    x = O.synthetic_series(1000, 4, 4, fs, seed=5)
+    m = sc.Multitaper(x, fs, 2, time_window_duration=1.0)
+    ref = sc.Connectivity.from_multitaper(m).compute(["coherence_magnitude", "pairwise_spectral_granger_prediction"])
+    coef = m.fft()
+    c1 = sc.Connectivity(fourier_coefficients=coef, frequencies=m.frequencies, time=m.time)
+    assert c1._mt is m
+    c2 = sc.Connectivity(fourier_coefficients=coef.cpu().numpy(), frequencies=m.frequencies, time=m.time)
+    assert c2._mt is None and c2._hermitian
+    coef2 = m.fft()
+    coef2[0, 0, 0, 3, 1] += 0.5  # modified in place: no longer the transform of a real series
+    c3 = sc.Connectivity(fourier_coefficients=coef2)
+    assert c3._mt is None and not c3._hermitian
+    for c in (c1, c2):
+        got = c.compute(list(ref))
+        for k in ref:
+            assert_parity(got[k], ref[k], 2e-6, k)
+    assert np.isfinite(c3.coherence_magnitude()[..., 0, 1]).all()
+
+
+def test_granger_and_mvar_general_two_sided_coefficients(sc):
+    """Coefficients that are NOT conjugate symmetric (e.g. of complex-valued series) take the general kernels:
+    full-circle Wilson iteration, no symmetry shortcuts."""
+    rng = np.random.default_rng(12)
+    n_f = 48
+    # a stable complex AR(1)-like colouring so that the spectra are smooth and well conditioned
+    white = rng.standard_normal((2, 40, 2, n_f, 3)) + 1j * rng.standard_normal((2, 40, 2, n_f, 3))
+    shape = 1.0 / (1.0 - 0.5 * np.exp(-2j * np.pi * np.arange(n_f) / n_f))
+    coef = white * shape[None, None, None, :, None]
+    coef[..., 1] += 0.4 * coef[..., 0] * np.exp(-2j * np.pi * np.arange(n_f) / n_f)[None, None, None, :]
+    c = sc.Connectivity(coef)
+    assert not c._hermitian
+    csm, pw = O.expected_csm(coef), O.power(coef)
+    ref, its = O.pairwise_granger(csm, pw, return_iterations=True)
+    got = c.pairwise_spectral_granger_prediction()
+    assert_parity(got, ref, 2e-5, "granger, general two-sided")
+    h, sigma = O.mvar_transfer_function(csm)
+    assert_parity(c.directed_transfer_function(), O.directed_transfer_function(h), 2e-5, "DTF, general two-sided")
