@@ -79,7 +79,7 @@ const char* sc_last_error(void);
  *  scale    multiplies the result (1/fs in the reference, :1405)
  *  twiddle  c64 [nfft], exp(-2 pi i q/nfft)
  *  layout   SC_LAYOUT_PLANAR: out float32 [B][n_freq_out][2][n_reduce][S] via map[6]
- *           SC_LAYOUT_REFERENCE: out c64 (W_total?,T,K,n_freq_out,S) indexed by output window
+ *           SC_LAYOUT_REFERENCE: out c64 (windows,T,K,n_freq_out,S), row = output window index
  *  n_freq_out  number of leading bins written (nfft//2+1 or nfft)
  *  workspace   only for windows too long for shared memory: sc_mt_fft_workspace_bytes()
  */
