@@ -207,8 +207,17 @@ class Connectivity:
             wc = max(1, min(n_win, self._max_chunk_bytes // max(per_window, 1)))
         else:
             wc = n_win
-        for w0 in range(0, n_win, wc):
-            w1 = min(n_win, w0 + wc)
+        # window ranges: full chunks, then (host output only) a geometrically shrinking tail so that the last
+        # device->host copy, which nothing can overlap, is small
+        bounds, w0 = [], 0
+        while w0 < n_win:
+            left = n_win - w0
+            size = min(wc, left)
+            if self._output == "numpy" and time_kept and left <= wc and left > 1:
+                size = (left + 1) // 2
+            bounds.append((w0, w0 + size))
+            w0 += size
+        for w0, w1 in bounds:
             mapping, kept, nb, nr = expectation_map((w1 - w0, n_trials, n_tapers), expectation_type)
             xp = torch.empty((nb, n_freq, 2, nr, n_sig), dtype=torch.float32, device=self._device)
             if self._mt is not None:
