@@ -22,7 +22,7 @@ constexpr double kTailRest = 32.0;   // closed-form tail once the non-constant p
                                      // kTailRest * tol: those modes converge quadratically, so what is left of
                                      // them after the update is far below tol (measured deviation from the
                                      // reference's own final iterate: 2e-8 relative at 10 * tol)
-constexpr float kSwitch = 5e-3f;     // hand over to fp64 once the non-constant part of the update (scaled
+constexpr float kSwitch = 1.5e-3f;     // hand over to fp64 once the non-constant part of the update (scaled
                                      // units, |G'| ~ 1) is below this: the iteration converges quadratically
                                      // in those modes, so two fp64 iterations then reach 1e-8
 
