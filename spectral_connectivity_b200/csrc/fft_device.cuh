@@ -272,14 +272,22 @@ template <int N, int... RS> struct ScStaticTw<ScStaticPlan<N, RS...>> {
     static constexpr int count = ScTwCount<1, RS...>::value;
 };
 
-template <typename R, int N, int LS, int RADIX>
-SC_HD void sc_static_item(const cx<R>* src, cx<R>* dst, int j, const cx<R>* tws, bool inv) {
-    constexpr int M = N / RADIX;
-    const int k = LS == 1 ? 0 : (LS == M ? j : j % LS);
-    cx<R> v[RADIX];
+// Twiddle factors of one butterfly (stage with sub-length LS > 1, k = j % LS): v[t] *= W^(t*k).
+// POW = false reads the RADIX-1 factors from the stage table; POW = true reads only W^k and forms
+// the higher powers by multiplication (w[t] = w[t/2] * w[t - t/2], depth log2 t) -- RADIX-2 fewer
+// shared-memory loads per butterfly for RADIX-2 complex multiplies and a few ulp of accuracy, for
+// shared-memory-bound callers that do not need the last bits (the fp32 phase of the Wilson iteration).
+template <typename R, int RADIX, int LS, bool POW>
+SC_HD void sc_static_twiddle(cx<R>* v, const cx<R>* tws, int k, bool inv) {
+    if (POW) {
+        cx<R> w[RADIX];
+        w[1] = tws[k];
+        if (inv) w[1].y = -w[1].y;
 #pragma unroll
-    for (int t = 0; t < RADIX; ++t) v[t] = src[j + t * M];
-    if (LS > 1) {
+        for (int t = 2; t < RADIX; ++t) w[t] = cmul(w[t / 2], w[t - t / 2]);
+#pragma unroll
+        for (int t = 1; t < RADIX; ++t) v[t] = cmul(v[t], w[t]);
+    } else {
 #pragma unroll
         for (int t = 1; t < RADIX; ++t) {
             cx<R> w = tws[(t - 1) * LS + k];
@@ -287,10 +295,76 @@ SC_HD void sc_static_item(const cx<R>* src, cx<R>* dst, int j, const cx<R>* tws,
             v[t] = cmul(v[t], w);
         }
     }
+}
+
+template <typename R, int N, int LS, int RADIX, bool POW = false>
+SC_HD void sc_static_item(const cx<R>* src, cx<R>* dst, int j, const cx<R>* tws, bool inv) {
+    constexpr int M = N / RADIX;
+    const int k = LS == 1 ? 0 : (LS == M ? j : j % LS);
+    cx<R> v[RADIX];
+#pragma unroll
+    for (int t = 0; t < RADIX; ++t) v[t] = src[j + t * M];
+    if (LS > 1) sc_static_twiddle<R, RADIX, LS, POW>(v, tws, k, inv);
     sc_dft<R, RADIX>(v, inv, (const cx<R>*)0, N);
     const int ob = (j - k) * RADIX + k;
 #pragma unroll
     for (int q = 0; q < RADIX; ++q) dst[ob + q * LS] = v[q];
+}
+
+// forward DFT of RADIX points whose upper half (v[RADIX/2..]) is zero; only radix 10 has a shortcut
+template <typename R, int RADIX>
+SC_HD void sc_dft_lowhalf(cx<R>* v) {
+    if (RADIX == 10) {
+        const R wc[5] = {(R)1.0, (R)0.80901699437494742410229341718282, (R)0.30901699437494742410229341718282,
+                         (R)-0.30901699437494742410229341718282, (R)-0.80901699437494742410229341718282};
+        const R ws[5] = {(R)0.0, (R)0.58778525229247312916870595463907, (R)0.95105651629515357211643933337938,
+                         (R)0.95105651629515357211643933337938, (R)0.58778525229247312916870595463907};
+        cx<R> e[5], o[5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            e[a] = v[a];
+            o[a] = a > 0 ? cmul(v[a], cmake<R>(wc[a], -ws[a])) : v[a];
+        }
+        sc_dft5(e, false);
+        sc_dft5(o, false);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            v[2 * q] = e[q];
+            v[2 * q + 1] = o[q];
+        }
+    } else {
+#pragma unroll
+        for (int t = RADIX / 2; t < RADIX; ++t) v[t] = cmake<R>((R)0, (R)0);
+        sc_dft<R, RADIX>(v, false, (const cx<R>*)0, 0);
+    }
+}
+
+// Fused middle of inverse-FFT -> elementwise window -> forward-FFT for a plan whose first and last radix
+// are equal: butterfly j of the LAST inverse stage produces the samples n = j + q*M (q < RADIX), exactly
+// the inputs of butterfly j of the FIRST forward stage, so the window is applied in registers and one
+// write + one read of the whole sequence (and a barrier) disappear.  win(bb, n, value) returns the
+// windowed sample; samples n >= KCUT are known to be windowed to zero (KCUT = N keeps all).
+template <typename R, int N, int RADIX, int KCUT, bool POW, typename WIN>
+SC_HD void sc_static_mid_item(const cx<R>* src, cx<R>* dst, int bb, int j, const cx<R>* tws_last, WIN& win) {
+    constexpr int M = N / RADIX;
+    constexpr bool HALF = (KCUT % M == 0) && (KCUT / M == RADIX / 2) && (RADIX % 2 == 0);
+    cx<R> v[RADIX];
+#pragma unroll
+    for (int t = 0; t < RADIX; ++t) v[t] = src[j + t * M];
+    sc_static_twiddle<R, RADIX, M, POW>(v, tws_last, j, true);
+    sc_dft<R, RADIX>(v, true, (const cx<R>*)0, N);
+    if (HALF) {
+#pragma unroll
+        for (int q = 0; q < RADIX / 2; ++q) v[q] = win(bb, j + q * M, v[q]);
+        sc_dft_lowhalf<R, RADIX>(v);
+    } else {
+#pragma unroll
+        for (int q = 0; q < RADIX; ++q)
+            v[q] = (j + q * M < KCUT) ? win(bb, j + q * M, v[q]) : cmake<R>((R)0, (R)0);
+        sc_dft<R, RADIX>(v, false, (const cx<R>*)0, N);
+    }
+#pragma unroll
+    for (int q = 0; q < RADIX; ++q) dst[j * RADIX + q] = v[q];
 }
 
 // fill the stage tables of one stage from the flat table tw[q] = exp(-2 pi i q/N)
@@ -351,6 +425,47 @@ template <typename R, int N, int... RS> struct ScStaticFft<R, ScStaticPlan<N, RS
     }
     static SC_HD void fill(cx<R>* tws, const cx<R>* tw, int tid, int nthreads) {
         ScStaticStages<R, N, 1, RS...>::fill(tws, tw, tid, nthreads);
+    }
+};
+
+// inverse FFT -> window (zero beyond KCUT) -> forward FFT of NB sequences at a + b*N, three-stage plans
+// with equal outer radices; 5 shared-memory passes instead of 7 (see sc_static_mid_item).  Both transforms
+// unnormalised; returns the buffer that holds the forward result (always b).
+template <typename R, typename PLAN, int KCUT, bool POW = false> struct ScStaticConv {
+    static constexpr bool supported = false;
+    template <int NB, typename SYNC, typename WIN>  // never called: callers branch on `supported`
+    static SC_HD cx<R>* run(cx<R>* a, cx<R>*, const cx<R>*, int, int, SYNC, WIN) { return a; }
+};
+template <typename R, int N, int R0, int R1, int KCUT, bool POW>
+struct ScStaticConv<R, ScStaticPlan<N, R0, R1, R0>, KCUT, POW> {
+    static constexpr bool supported = true;
+    template <int LS, int RADIX, int NB>
+    static SC_HD void stage(const cx<R>* src, cx<R>* dst, const cx<R>* tws, bool inv, int tid, int nthreads) {
+        constexpr int M = N / RADIX;
+        for (int idx = tid; idx < NB * M; idx += nthreads) {
+            const int bb = idx / M, j = idx % M;
+            sc_static_item<R, N, LS, RADIX, POW>(src + bb * N, dst + bb * N, j, tws, inv);
+        }
+    }
+    template <int NB, typename SYNC, typename WIN>
+    static SC_HD cx<R>* run(cx<R>* a, cx<R>* b, const cx<R>* tws, int tid, int nthreads, SYNC sync, WIN win) {
+        const cx<R>* tw1 = tws;                  // stage 1 table (LS = R0)
+        const cx<R>* tw2 = tws + (R1 - 1) * R0;  // stage 2 table (LS = R0*R1)
+        stage<1, R0, NB>(a, b, tws, true, tid, nthreads);
+        sync();
+        stage<R0, R1, NB>(b, a, tw1, true, tid, nthreads);
+        sync();
+        constexpr int M = N / R0;
+        for (int idx = tid; idx < NB * M; idx += nthreads) {
+            const int bb = idx / M, j = idx % M;
+            sc_static_mid_item<R, N, R0, KCUT, POW>(a + bb * N, b + bb * N, bb, j, tw2, win);
+        }
+        sync();
+        stage<R0, R1, NB>(b, a, tw1, false, tid, nthreads);
+        sync();
+        stage<R0 * R1, R0, NB>(a, b, tw2, false, tid, nthreads);
+        sync();
+        return b;
     }
 };
 

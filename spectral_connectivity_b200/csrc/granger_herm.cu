@@ -5,10 +5,14 @@
 //  * only the nfft/2+1 non-negative bins are ever evaluated; the 2x2 factor G(f) and the three
 //    independent entries of S(f) live in REGISTERS (each thread owns FPT frequencies), so the
 //    only shared-memory traffic is the FFT ping-pong buffer;
-//  * the linear predictor B = G^-1 S G^-H + I is Hermitian with real even diagonal, so its inverse
-//    transform is real: c00 + i*c11 come out of ONE complex FFT, c01 out of a second
-//    (c10[k] = c01[-k]); the four causal sequences go back through TWO complex FFTs packed two
-//    real sequences each.  4 complex FFTs per iteration instead of the reference's 8;
+//  * the linear predictor B = G^-1 S G^-H + I is Hermitian with B(-f) = conj B(f), so its four lag sequences
+//    are real: Z1 = B00 + i B11 and Z2 = B01 + i B10 are inverse-transformed by TWO complex FFTs into
+//    c00 + i c11 and c01 + i c10, the plus operator is then elementwise on those packed sequences, and two
+//    forward FFTs give P00 + i P11 and P01 + i P10, unpacked by Hermitian symmetry: 4 complex FFTs per
+//    iteration instead of the reference's 8;
+//  * for three-stage plans with equal outer radices (nfft = 1000 = 10*10*10) the last inverse stage, the
+//    plus operator and the first forward stage run in registers (ScStaticConv), 5 shared-memory passes per
+//    inverse+forward pair instead of 7; the fp32 phase forms stage twiddles as powers of the first one;
 //  * the Granger epilogue (transfer function, noise covariance, log ratio) is evaluated from the
 //    registers and written straight into the (B, Fnn, S, S) output.
 #include "wilson_common.cuh"
@@ -26,12 +30,19 @@ constexpr float kSwitch = 1.5e-3f;     // hand over to fp64 once the non-constan
                                      // units, |G'| ~ 1) is below this: the iteration converges quadratically
                                      // in those modes, so two fp64 iterations then reach 1e-8
 
+#ifndef SC_GRANGER_POW_TWIDDLES
+#define SC_GRANGER_POW_TWIDDLES 1  // fp32 phase: stage twiddles as powers of the first (fewer shared loads)
+#endif
+
 struct CtaSync {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
 // FFT policies: runtime plan (any length) or a compile-time plan (fft_device.cuh).
 struct DynFft {
+    template <typename R> struct Fused { static constexpr bool value = false; };
+    template <typename R, typename WIN>
+    static __device__ __forceinline__ cx<R>* conv2(cx<R>* a, cx<R>*, const cx<R>*, WIN) { return a; }
     static __host__ __device__ int tw_entries(int n) { return n; }
     template <typename R>
     static __device__ __forceinline__ void fill(cx<R>* tws, const cx<R>* tw, int n) {
@@ -44,6 +55,17 @@ struct DynFft {
     }
 };
 template <typename PLAN> struct StatFft {
+    static constexpr int kCut = (PLAN::n + 1) / 2;  // the plus operator keeps lags [0, kCut)
+    template <typename R> struct Fused {
+        static constexpr bool pow = SC_GRANGER_POW_TWIDDLES && sizeof(R) == 4;
+        static constexpr bool value = ScStaticConv<R, PLAN, kCut, pow>::supported;
+    };
+    // inverse FFT -> window -> forward FFT of the two packed sequences (fft_device.cuh: ScStaticConv)
+    template <typename R, typename WIN>
+    static __device__ __forceinline__ cx<R>* conv2(cx<R>* a, cx<R>* b, const cx<R>* tws, WIN win) {
+        return ScStaticConv<R, PLAN, kCut, Fused<R>::pow>::template run<2>(a, b, tws, threadIdx.x, kThreads, CtaSync(),
+                                                                         win);
+    }
     static __host__ __device__ int tw_entries(int) { return ScStaticTw<PLAN>::count; }
     template <typename R>
     static __device__ __forceinline__ void fill(cx<R>* tws, const cx<R>* tw, int) {
@@ -61,6 +83,27 @@ template <> struct RealOps<double> {
 };
 template <> struct RealOps<float> {
     static __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
+};
+
+// The plus operator (mpd.py:129-142) on the packed lag sequences z1 = c00 + i c11 (bb = 0) and
+// z2 = c01 + i c10 (bb = 1): scale by 1/N, halve lag 0, zero the lag-0 lower triangle (c10[0]); lags >= kcut
+// are zeroed by the caller.  Also records the lag-0 residual of G^-1 S G^-H - I.
+template <typename R> struct PlusWindow {
+    R inv_n;
+    R* lag0;
+    __device__ __forceinline__ cx<R> operator()(int bb, int k, cx<R> z) const {
+        if (k == 0) {
+            const R h = (R)0.5 * inv_n;
+            if (bb == 0) {
+                lag0[0] = z.x * inv_n - (R)2;
+                lag0[2] = z.y * inv_n - (R)2;
+                return cmake<R>(z.x * h, z.y * h);
+            }
+            lag0[1] = z.x * inv_n;
+            return cmake<R>(z.x * h, (R)0);
+        }
+        return cmake<R>(z.x * inv_n, z.y * inv_n);
+    }
 };
 
 // One Wilson iteration on the half spectrum held in registers.  On return stat[0] = max |dG|^2 of
@@ -99,39 +142,41 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
             // t0 . conj(r1) = -t00*conj(v0) + t01*conj(v1)
             const cx<R> b01 = cmake<R>(-(t00.x * v0.x + t00.y * v0.y) + (t01.x * v1.x + t01.y * v1.y),
                                        -(t00.y * v0.x - t00.x * v0.y) + (t01.y * v1.x - t01.x * v1.y));
+            // Z1 = B00 + i B11, Z2 = B01 + i B10 with B10 = conj(B01) and B(-f) = conj(B(f)): the inverse
+            // transforms are z1 = c00 + i c11 and z2 = c01 + i c10 (all four lag sequences are real)
             const int fm = f == 0 ? 0 : N - f;
             ZA[f] = cmake<R>(b00, b11);
             ZA[fm] = cmake<R>(b00, b11);
-            ZA[N + fm] = cconj(b01);
-            ZA[N + f] = b01;  // last: for f == fm (DC, Nyquist) the imaginary part is ~0 either way
-        }
-    }
-    __syncthreads();
-    // ---- plus operator (mpd.py:129-142) on the real sequences, packed for the forward FFTs ----
-    cx<R>* c = FFT::template run2<R>(ZA, ZB, plan, tw, true);
-    cx<R>* o = (c == ZA) ? ZB : ZA;
-    const R inv_n = (R)1 / (R)N;
-    const int kcut = (N + 1) / 2;
-    for (int k = threadIdx.x; k < N; k += kThreads) {
-        cx<R> y1 = cmake<R>((R)0, (R)0), y2 = y1;
-        if (k < kcut) {
-            const R w = k == 0 ? (R)0.5 * inv_n : inv_n;
-            const cx<R> z1 = c[k];                  // c00[k] + i c11[k]
-            const R c01 = c[N + k].x;
-            const R c10 = k == 0 ? (R)0 : c[N + (N - k)].x;  // c10[k] = c01[-k]; zeroed at lag 0
-            y1 = cmake<R>(z1.x * w, c01 * w);       // p00 + i p01
-            y2 = cmake<R>(c10 * w, z1.y * w);       // p10 + i p11
-            if (k == 0) {
-                lag0[0] = z1.x * inv_n - (R)2;
-                lag0[1] = c01 * inv_n;
-                lag0[2] = z1.y * inv_n - (R)2;
+            if (f == fm) {
+                ZA[N + f] = cmake<R>(b01.x, b01.x);  // DC / Nyquist: B01 is real
+            } else {
+                ZA[N + f] = cmake<R>(b01.x + b01.y, b01.x + b01.y);
+                ZA[N + fm] = cmake<R>(b01.x - b01.y, b01.x - b01.y);
             }
         }
-        o[k] = y1;
-        o[N + k] = y2;
     }
     __syncthreads();
-    const cx<R>* Q = FFT::template run2<R>(o, c, plan, tw, false);
+    // ---- plus operator (mpd.py:129-142) between the inverse and the forward transforms ----
+    const PlusWindow<R> win = {(R)1 / (R)N, lag0};
+    const cx<R>* Q;
+    if (FFT::template Fused<R>::value) {
+        Q = FFT::template conv2<R>(ZA, ZB, tw, win);
+    } else {
+        cx<R>* c = FFT::template run2<R>(ZA, ZB, plan, tw, true);
+        cx<R>* o = (c == ZA) ? ZB : ZA;
+        const int kcut = (N + 1) / 2;
+        for (int k = threadIdx.x; k < N; k += kThreads) {
+            cx<R> y1 = cmake<R>((R)0, (R)0), y2 = y1;
+            if (k < kcut) {
+                y1 = win(0, k, c[k]);
+                y2 = win(1, k, c[N + k]);
+            }
+            o[k] = y1;
+            o[N + k] = y2;
+        }
+        __syncthreads();
+        Q = FFT::template run2<R>(o, c, plan, tw, false);
+    }
     // ---- G <- G P (mpd.py:305-307) ----
     R err2 = (R)0, rest2 = (R)0, c00 = (R)0, c10 = (R)0, c01m = (R)0, c11m = (R)0;
     const R h00 = (R)0.5 * lag0[0], h01 = (R)0.5 * lag0[1], h11 = (R)0.5 * lag0[2];  // P0 - I
@@ -142,10 +187,11 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
             const int fm = f == 0 ? 0 : N - f;
             const cx<R> a1 = Q[f], m1 = Q[fm], a2 = Q[N + f], m2 = Q[N + fm];
             const R h = (R)0.5;
+            // Y1 = P00 + i P11, Y2 = P01 + i P10 (spectra of real sequences): even / odd Hermitian parts
             const cx<R> p00 = cmake<R>(h * (a1.x + m1.x), h * (a1.y - m1.y));
-            const cx<R> p01 = cmake<R>(h * (a1.y + m1.y), h * (m1.x - a1.x));
-            const cx<R> p10 = cmake<R>(h * (a2.x + m2.x), h * (a2.y - m2.y));
-            const cx<R> p11 = cmake<R>(h * (a2.y + m2.y), h * (m2.x - a2.x));
+            const cx<R> p11 = cmake<R>(h * (a1.y + m1.y), h * (m1.x - a1.x));
+            const cx<R> p01 = cmake<R>(h * (a2.x + m2.x), h * (a2.y - m2.y));
+            const cx<R> p10 = cmake<R>(h * (a2.y + m2.y), h * (m2.x - a2.x));
             const cx<R> n00 = cadd(cmul(g00[q], p00), cmul(g01[q], p10));
             const cx<R> n01 = cadd(cmul(g00[q], p01), cmul(g01[q], p11));
             const cx<R> n10 = cadd(cmul(g10[q], p00), cmul(g11[q], p10));

@@ -82,6 +82,48 @@ extern "C" int fft_static_f64(double* data, int n, int inverse) {
     return -1;
 }
 
+// inverse FFT -> window (w[n] for n < 500, else 0; batch 1 additionally drops the imaginary part at n = 0)
+// -> forward FFT of 2 sequences of length 1000 through the fused three-stage path
+template <typename R> struct TestWin {
+    const R* w;
+    SC_HD cx<R> operator()(int bb, int n, cx<R> v) const {
+        cx<R> r = cmake<R>(v.x * w[n], v.y * w[n]);
+        if (bb == 1 && n == 0) r.y = (R)0;
+        return r;
+    }
+};
+template <typename R, bool POW>
+static int run_conv(R* data, const R* w) {
+    const int n = 1000;
+    typedef ScStaticFft<R, ScPlan1000> F;
+    typedef ScStaticConv<R, ScPlan1000, 500, POW> C;
+    static_assert(C::supported, "plan 1000 supports the fused path");
+    static_assert(!ScStaticConv<R, ScPlan120, 60, POW>::supported, "plan 120 does not");
+    std::vector<cx<R>> a(2 * n), b(2 * n), tw(n), tws(F::tw_count + 1);
+    for (int i = 0; i < 2 * n; ++i) {
+        a[i].x = data[2 * i];
+        a[i].y = data[2 * i + 1];
+    }
+    for (int i = 0; i < n; ++i) {
+        tw[i].x = (R)cos(-2.0 * M_PI * i / n);
+        tw[i].y = (R)sin(-2.0 * M_PI * i / n);
+    }
+    F::fill(tws.data(), tw.data(), 0, 1);
+    TestWin<R> win{w};
+    cx<R>* res = C::template run<2>(a.data(), b.data(), tws.data(), 0, 1, [] {}, win);
+    for (int i = 0; i < 2 * n; ++i) {
+        data[2 * i] = res[i].x;
+        data[2 * i + 1] = res[i].y;
+    }
+    return 0;
+}
+extern "C" int fft_conv_f64(double* data, const double* w, int pow_twiddles) {
+    return pow_twiddles ? run_conv<double, true>(data, w) : run_conv<double, false>(data, w);
+}
+extern "C" int fft_conv_f32(float* data, const float* w, int pow_twiddles) {
+    return pow_twiddles ? run_conv<float, true>(data, w) : run_conv<float, false>(data, w);
+}
+
 extern "C" int fft_plan(int n, int* radices) {
     ScFftPlan plan;
     if (sc_fft_make_plan(n, &plan)) return -1;

@@ -66,6 +66,30 @@ def test_fft_static_plan(lib, n, inverse):
     assert np.abs(buf.view(np.complex128) - ref).max() <= 1e-12 * np.abs(ref).max() * 10
 
 
+@pytest.mark.parametrize("pow_twiddles", [0, 1])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fused_inverse_window_forward(lib, dtype, pow_twiddles):
+    """ScStaticConv (last inverse stage + window + first forward stage in registers) == ifft, window, fft."""
+    n = 1000
+    rng = np.random.default_rng(7 + pow_twiddles)
+    z = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))
+    w = rng.uniform(0.5, 1.5, n)
+    ref = np.fft.ifft(z, axis=-1) * n
+    ref[:, 500:] = 0
+    ref[:, :500] *= w[:500]
+    ref[1, 0] = ref[1, 0].real
+    ref = np.fft.fft(ref, axis=-1)
+    cdt = np.complex128 if dtype is np.float64 else np.complex64
+    buf = np.ascontiguousarray(z.astype(cdt).view(dtype).copy())
+    wv = np.ascontiguousarray(w.astype(dtype))
+    ct = ctypes.c_double if dtype is np.float64 else ctypes.c_float
+    fn = lib.fft_conv_f64 if dtype is np.float64 else lib.fft_conv_f32
+    assert fn(buf.ctypes.data_as(ctypes.POINTER(ct)), wv.ctypes.data_as(ctypes.POINTER(ct)), pow_twiddles) == 0
+    got = buf.view(cdt).reshape(2, n)
+    tol = 1e-12 if dtype is np.float64 else (6e-6 if pow_twiddles else 3e-6)
+    assert np.abs(got - ref).max() <= tol * np.abs(ref).max()
+
+
 def test_plan_1000(lib):
     r = (ctypes.c_int * 32)()
     assert lib.fft_plan(1000, r) == 3 and list(r[:3]) == [10, 10, 10]
