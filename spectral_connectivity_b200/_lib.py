@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsc_b200.so")
+LIB_PATH = os.environ.get("SC_B200_LIB") or os.path.join(_HERE, "libsc_b200.so")  # override: kernel experiments
 
 # symbol -> (restype, argtypes); must list every function of include/sc_b200.h
 _P = c_void_p

@@ -12,7 +12,7 @@
 //    iteration instead of the reference's 8;
 //  * for three-stage plans with equal outer radices (nfft = 1000 = 10*10*10) the last inverse stage, the
 //    plus operator and the first forward stage run in registers (ScStaticConv), 5 shared-memory passes per
-//    inverse+forward pair instead of 7; the fp32 phase forms stage twiddles as powers of the first one;
+//    inverse+forward pair instead of 7;
 //  * the Granger epilogue (transfer function, noise covariance, log ratio) is evaluated from the
 //    registers and written straight into the (B, Fnn, S, S) output.
 #include "wilson_common.cuh"
@@ -31,7 +31,8 @@ constexpr float kSwitch = 1.5e-3f;     // hand over to fp64 once the non-constan
                                      // in those modes, so two fp64 iterations then reach 1e-8
 
 #ifndef SC_GRANGER_POW_TWIDDLES
-#define SC_GRANGER_POW_TWIDDLES 1  // fp32 phase: stage twiddles as powers of the first (fewer shared loads)
+#define SC_GRANGER_POW_TWIDDLES 0  // stage twiddles as powers of the first one (fewer shared loads, more
+                                   // multiplies): 1 = fp32 phase, 2 = both.  Measured neutral on B200 -> off
 #endif
 
 struct CtaSync {
@@ -40,6 +41,7 @@ struct CtaSync {
 
 // FFT policies: runtime plan (any length) or a compile-time plan (fft_device.cuh).
 struct DynFft {
+    static constexpr bool kPrefetch = false;  // runtime-plan kernels are at the register cap already
     template <typename R> struct Fused { static constexpr bool value = false; };
     template <typename R, typename WIN>
     static __device__ __forceinline__ cx<R>* conv2(cx<R>* a, cx<R>*, const cx<R>*, WIN) { return a; }
@@ -55,9 +57,10 @@ struct DynFft {
     }
 };
 template <typename PLAN> struct StatFft {
+    static constexpr bool kPrefetch = true;  // fetch the next problem's spectrum under the epilogue
     static constexpr int kCut = (PLAN::n + 1) / 2;  // the plus operator keeps lags [0, kCut)
     template <typename R> struct Fused {
-        static constexpr bool pow = SC_GRANGER_POW_TWIDDLES && sizeof(R) == 4;
+        static constexpr bool pow = SC_GRANGER_POW_TWIDDLES >= 2 || (SC_GRANGER_POW_TWIDDLES == 1 && sizeof(R) == 4);
         static constexpr bool value = ScStaticConv<R, PLAN, kCut, pow>::supported;
     };
     // inverse FFT -> window -> forward FFT of the two packed sequences (fft_device.cuh: ScStaticConv)
@@ -84,6 +87,20 @@ template <> struct RealOps<double> {
 template <> struct RealOps<float> {
     static __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
 };
+
+// log(total) - log(total - part) of connectivity.py:1773-1779 (0 -> eps in the denominator, non-positive
+// results -> NaN), rounded to the float32 output: the difference total - part is formed in fp64 exactly as the
+// reference does, the logarithm of the RATIO is then taken in single precision -- through log1p when the
+// ratio is close to one so that small Granger values keep their relative accuracy.
+__device__ __forceinline__ float log_ratio(double total, double part) {
+    double rest = total - part;
+    if (rest == 0.0) rest = kEps64;
+    const double ratio = rest / total;
+    float gc;
+    if (ratio >= 0.5) gc = -log1pf((float)((rest - total) / total));  // = -log1p(-(total - rest)/total)
+    else gc = -logf((float)ratio);
+    return gc > 0.f ? gc : __int_as_float(0x7fc00000);
+}
 
 // The plus operator (mpd.py:129-142) on the packed lag sequences z1 = c00 + i c11 (bb = 0) and
 // z2 = c01 + i c10 (bb = 1): scale by 1/N, halve lag 0, zero the lag-0 lower triangle (c10[0]); lags >= kcut
@@ -221,6 +238,11 @@ template <int FPT, typename FFT>
 __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[6 * kWarps];
+    __shared__ double tail_sh[3];
+    __shared__ int tail_it[2];
+    __shared__ unsigned redf[2 * kWarps];
+    __shared__ unsigned long long redd[2 * 6 * kWarps];
+    int phase_f = 0, phase_d = 0;
     const int N = p.nfft;
     const int fnn = N / 2 + 1;
     __shared__ double lag0_sh[3];
@@ -239,20 +261,20 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
     const float fnan = __int_as_float(0x7fc00000);
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-    for (long long prob = blockIdx.x; prob < nprob; prob += gridDim.x) {
-        const long long b = prob / npairs;
-        const long long pk = prob % npairs;
-        int pi, pj;
+    // the three independent entries of S(f), f = 0..nfft/2, of problem `prob` (pair pk of window b)
+    float s00[FPT], s11[FPT];
+    float2 s01[FPT];
+    auto pair_of = [&](long long prob, long long& b, long long& pk, int& pi, int& pj) {
+        b = prob / npairs;
+        pk = prob % npairs;
         if (p.pairs) {
             pi = p.pairs[2 * pk];
             pj = p.pairs[2 * pk + 1];
         } else {
             decode_pair(pk, p.S, pi, pj);
         }
-        // ---- load the three independent entries of S(f), f = 0..nfft/2 ----------
-        float s00[FPT], s11[FPT];
-        float2 s01[FPT];
-        double a[3] = {0.0, 0.0, 0.0};
+    };
+    auto load_s = [&](long long b, int pi, int pj) {
 #pragma unroll
         for (int q = 0; q < FPT; ++q) {
             const int f = threadIdx.x + q * kThreads;
@@ -262,6 +284,25 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                 s00[q] = __ldg(&m[(size_t)pi * p.S + pi]).x;
                 s11[q] = __ldg(&m[(size_t)pj * p.S + pj]).x;
                 s01[q] = __ldg(&m[(size_t)pi * p.S + pj]);
+            }
+        }
+    };
+    long long b = 0, pk = 0, nb_ = 0, npk = 0;
+    int pi = 0, pj = 0, npi = 0, npj = 0;
+    if (blockIdx.x < nprob) {
+        pair_of(blockIdx.x, b, pk, pi, pj);
+        load_s(b, pi, pj);
+    }
+    for (long long prob = blockIdx.x; prob < nprob; prob += gridDim.x, b = nb_, pk = npk, pi = npi, pj = npj) {
+        if (!FFT::kPrefetch && prob != blockIdx.x) {
+            pair_of(prob, b, pk, pi, pj);
+            load_s(b, pi, pj);
+        }
+        double a[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < FPT; ++q) {
+            const int f = threadIdx.x + q * kThreads;
+            if (f < fnn) {
                 const double w = (f == 0 || 2 * f == N) ? 1.0 : 2.0;  // bins f and nfft-f
                 a[0] += w * s00[q]; a[1] += w * s01[q].x; a[2] += w * s11[q];
             }
@@ -299,8 +340,8 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                     float stf[6];
                     herm_iteration<float, FPT, FFT>(f00, f01, f10, f11, s00, s11, s01, r0 * r0, r1 * r1, r0 * r1, ZAf, ZBf,
                                                     p.plan, twsf, N, fnn, lag0f_sh, stf);
-                    double e2 = stf[1];  // update minus its constant-matrix (tail) part
-                    const float errf = sqrtf((float)block_max(e2, red));  // also fences the buffers
+                    // update minus its constant-matrix (tail) part; the barrier inside also fences the buffers
+                    const float errf = sqrtf(block_max_nonneg(stf[1], redf, phase_f));
                     if (errf < kSwitch) {
                         ++it0;
                         break;
@@ -318,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                 double st[6];
                 herm_iteration<double, FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, 1.0, 1.0, 1.0, ZA, ZB, p.plan, tws, N, fnn,
                                                  lag0_sh, st);
-                block_maxn<6>(st, red);  // also fences ZA/ZB reuse
+                block_maxn_nonneg<6>(st, redd, phase_d);  // also fences ZA/ZB reuse
                 const double err = sqrt(st[0]);
                 it_done = it + 1;
                 converged = err < p.tol;
@@ -330,30 +371,43 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                     // constant upper-triangular 2x2 matrices P_j = I + upper_half(E_j), with
                     // E_j = C_j^-1 (I + e0) C_j^-T - I and C_{j+1} = C_j P_j.  That 2x2 recursion is run here
                     // exactly, up to the iterate at which the reference stops (first max|dG| < tol).
-                    const double e00 = lag0_sh[0], e01 = lag0_sh[1], e11 = lag0_sh[2];
-                    const double m00 = 1.0 + e00, m01 = e01, m11 = 1.0 + e11;  // I + e0 (symmetric)
-                    double ca = 1.0 + 0.5 * e00, cb = 0.5 * e01, cd_ = 1.0 + 0.5 * e11;  // C = P0 (already applied)
-                    double ta = 1.0, tb = 0.0, td = 1.0;                                 // T = product of later P_j
-                    const double n00 = sqrt(st[2]), n10 = sqrt(st[3]), n01 = sqrt(st[4]), n11 = sqrt(st[5]);
-                    while (it_done < p.max_iter) {
-                        // E = C^-1 M C^-T - I for upper-triangular C = [[ca, cb], [0, cd_]]
-                        const double ia = 1.0 / ca, id = 1.0 / cd_, ib = -cb * ia * id;
-                        const double r00 = ia * m00 + ib * m01, r01 = ia * m01 + ib * m11;  // row 0 of C^-1 M
-                        const double r11 = id * m11;                                          // row 1: (id*m01, id*m11)
-                        const double E00 = r00 * ia + r01 * ib - 1.0, E01 = r01 * id, E11 = r11 * id - 1.0;
-                        const double pa = 0.5 * E00, pb = 0.5 * E01, pd = 0.5 * E11;  // P_j - I
-                        // max |G_j (P_j - I)| with the column maxima of G at tail entry
-                        const double d0 = fmax(n00, n10) * fabs(pa);
-                        const double d1 = fmax(n00 * fabs(pb) + n01 * fabs(pd), n10 * fabs(pb) + n11 * fabs(pd));
-                        // T <- T P_j, C <- C P_j
-                        tb = ta * pb + tb * (1.0 + pd); ta *= 1.0 + pa; td *= 1.0 + pd;
-                        cb = ca * pb + cb * (1.0 + pd); ca *= 1.0 + pa; cd_ *= 1.0 + pd;
-                        ++it_done;
-                        if (fmax(d0, d1) < p.tol) {
-                            converged = true;
-                            break;
+                    // The scalar recursion is a chain of dependent fp64 divisions: one warp runs it and
+                    // broadcasts the accumulated factor T (the branch is uniform over the CTA).
+                    if (threadIdx.x < 32) {
+                        const double e00 = lag0_sh[0], e01 = lag0_sh[1], e11 = lag0_sh[2];
+                        const double m00 = 1.0 + e00, m01 = e01, m11 = 1.0 + e11;  // I + e0 (symmetric)
+                        double ca = 1.0 + 0.5 * e00, cb = 0.5 * e01, cd_ = 1.0 + 0.5 * e11;  // C = P0 (already applied)
+                        double ta = 1.0, tb = 0.0, td = 1.0;                                 // T = product of later P_j
+                        const double n00 = sqrt(st[2]), n10 = sqrt(st[3]), n01 = sqrt(st[4]), n11 = sqrt(st[5]);
+                        int itt = it_done, conv = 0;
+                        while (itt < p.max_iter) {
+                            // E = C^-1 M C^-T - I for upper-triangular C = [[ca, cb], [0, cd_]]
+                            const double ia = 1.0 / ca, id = 1.0 / cd_, ib = -cb * ia * id;
+                            const double r00 = ia * m00 + ib * m01, r01 = ia * m01 + ib * m11;  // row 0 of C^-1 M
+                            const double r11 = id * m11;                                          // row 1: (id*m01, id*m11)
+                            const double E00 = r00 * ia + r01 * ib - 1.0, E01 = r01 * id, E11 = r11 * id - 1.0;
+                            const double pa = 0.5 * E00, pb = 0.5 * E01, pd = 0.5 * E11;  // P_j - I
+                            // max |G_j (P_j - I)| with the column maxima of G at tail entry
+                            const double d0 = fmax(n00, n10) * fabs(pa);
+                            const double d1 = fmax(n00 * fabs(pb) + n01 * fabs(pd), n10 * fabs(pb) + n11 * fabs(pd));
+                            // T <- T P_j, C <- C P_j
+                            tb = ta * pb + tb * (1.0 + pd); ta *= 1.0 + pa; td *= 1.0 + pd;
+                            cb = ca * pb + cb * (1.0 + pd); ca *= 1.0 + pa; cd_ *= 1.0 + pd;
+                            ++itt;
+                            if (fmax(d0, d1) < p.tol) {
+                                conv = 1;
+                                break;
+                            }
+                        }
+                        if (threadIdx.x == 0) {
+                            tail_sh[0] = ta; tail_sh[1] = tb; tail_sh[2] = td;
+                            tail_it[0] = itt; tail_it[1] = conv;
                         }
                     }
+                    __syncthreads();
+                    const double ta = tail_sh[0], tb = tail_sh[1], td = tail_sh[2];
+                    it_done = tail_it[0];
+                    converged = tail_it[1] != 0;
 #pragma unroll
                     for (int q = 0; q < FPT; ++q) {
                         g01[q].x = g00[q].x * tb + g01[q].x * td; g01[q].y = g00[q].y * tb + g01[q].y * td;
@@ -369,21 +423,32 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
             if (p.iters) p.iters[pk * p.B + b] = it_done;
             if (p.flags) p.flags[pk * p.B + b] = flag;
         }
+        // the spectrum registers are free now: fetch the next problem's S under the epilogue
+        const int cpi = pi, cpj = pj;
+        const long long cb = b;
+        if (FFT::kPrefetch && prob + gridDim.x < nprob) {
+            pair_of(prob + gridDim.x, nb_, npk, npi, npj);
+            load_s(nb_, npi, npj);
+        }
         float* out = reinterpret_cast<float*>(p.out);
         if (flag & SC_FLAG_NOT_SPD) {
             for (int f = threadIdx.x; f < fnn; f += kThreads) {
-                float* m = out + ((size_t)b * fnn + f) * p.S * p.S;
-                m[(size_t)pi * p.S + pj] = fnan;
-                m[(size_t)pj * p.S + pi] = fnan;
+                float* m = out + ((size_t)cb * fnn + f) * p.S * p.S;
+                m[(size_t)cpi * p.S + cpj] = fnan;
+                m[(size_t)cpj * p.S + cpi] = fnan;
             }
             continue;
         }
         // ---- Granger epilogue (connectivity.py:1705-1709, 1739-1748, 1847-1848, 1773-1779) ----
+        float pw_i[FPT], pw_j[FPT];
         double h[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int q = 0; q < FPT; ++q) {
             const int f = threadIdx.x + q * kThreads;
+            pw_i[q] = 0.f; pw_j[q] = 0.f;
             if (f < fnn) {
+                pw_i[q] = __ldg(&p.power[((size_t)cb * p.F + f) * p.S + cpi]);
+                pw_j[q] = __ldg(&p.power[((size_t)cb * p.F + f) * p.S + cpj]);
                 const double w = (f == 0 || 2 * f == N) ? 1.0 : 2.0;
                 h[0] += w * g00[q].x; h[1] += w * g01[q].x; h[2] += w * g10[q].x; h[3] += w * g11[q].x;
             }
@@ -403,19 +468,11 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
             if (f < fnn) {
                 const cd t01 = cmake<double>(g00[q].x * v01 + g01[q].x * v11, g00[q].y * v01 + g01[q].y * v11);
                 const cd t10 = cmake<double>(g10[q].x * v00 + g11[q].x * v10, g10[q].y * v00 + g11[q].y * v10);
-                const double pw_i = __ldg(&p.power[((size_t)b * p.F + f) * p.S + pi]);
-                const double pw_j = __ldg(&p.power[((size_t)b * p.F + f) * p.S + pj]);
-                double in01 = pw_i - r01 * (t01.x * t01.x + t01.y * t01.y);
-                double in10 = pw_j - r10 * (t10.x * t10.x + t10.y * t10.y);
-                if (in01 == 0.0) in01 = kEps64;
-                if (in10 == 0.0) in10 = kEps64;
-                double gc01 = log(pw_i) - log(in01);
-                double gc10 = log(pw_j) - log(in10);
-                if (gc01 <= 0.0) gc01 = qnan;
-                if (gc10 <= 0.0) gc10 = qnan;
-                float* m = out + ((size_t)b * fnn + f) * p.S * p.S;
-                m[(size_t)pi * p.S + pj] = (float)gc01;
-                m[(size_t)pj * p.S + pi] = (float)gc10;
+                const float gc01 = log_ratio((double)pw_i[q], r01 * (t01.x * t01.x + t01.y * t01.y));
+                const float gc10 = log_ratio((double)pw_j[q], r10 * (t10.x * t10.x + t10.y * t10.y));
+                float* m = out + ((size_t)cb * fnn + f) * p.S * p.S;
+                m[(size_t)cpi * p.S + cpj] = gc01;
+                m[(size_t)cpj * p.S + cpi] = gc10;
             }
         }
     }

@@ -97,6 +97,49 @@ __device__ __forceinline__ double block_max(double v, double* red) {
     return m;
 }
 
+// ---- single-barrier maxima of NON-NEGATIVE values ---------------------------------------------------------
+// For non-negative IEEE numbers the unsigned bit pattern is order preserving, so the warp level is one
+// redux.sync (two for a 64-bit pattern: high words, then the low words of the lanes that hold the maximal high
+// word) instead of five shuffle+compare+select rounds.  Per-warp results go through a double-buffered shared
+// array (`phase` toggles), which makes ONE __syncthreads per call sufficient: a buffer is rewritten two calls
+// later, i.e. after every thread has passed the barrier of the call in between.  NaNs are dropped (fmax rule).
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long x) {
+    const unsigned hi = (unsigned)(x >> 32), lo = (unsigned)x;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
+
+__device__ __forceinline__ float block_max_nonneg(float v, unsigned* red /* [2 * kWarps] */, int& phase) {
+    const unsigned u = __reduce_max_sync(0xffffffffu, __float_as_uint(v == v ? v : 0.f));
+    unsigned* r = red + phase * kWarps;
+    phase ^= 1;
+    if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = u;
+    __syncthreads();
+    unsigned m = r[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) m = max(m, r[w]);
+    return __uint_as_float(m);
+}
+
+template <int NV>
+__device__ __forceinline__ void block_maxn_nonneg(double (&v)[NV], unsigned long long* red /* [2 * NV * kWarps] */,
+                                                  int& phase) {
+    static_assert(kWarps <= 32, "second level is one warp-wide redux");
+    unsigned long long* r = red + phase * NV * kWarps;
+    phase ^= 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const unsigned long long u = warp_max_u64((unsigned long long)__double_as_longlong(v[q] == v[q] ? v[q] : 0.0));
+        if (lane == 0) r[q * kWarps + warp] = u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NV; ++q)
+        v[q] = __longlong_as_double((long long)warp_max_u64(r[q * kWarps + (lane & (kWarps - 1))]));
+}
+
 __device__ __forceinline__ void decode_pair(long long k, long long S, int& i, int& j) {
     // k-th pair of combinations(range(S), 2) in lexicographic order
     const double t = 2.0 * S - 1.0;
