@@ -122,6 +122,21 @@ def load():
     return lib
 
 
+_SIDE_STREAMS = {}
+
+
+def side_stream(device, kind):
+    """Persistent per-device copy stream ("h2d" / "d2h").  A fresh torch.cuda.Stream() per call would walk
+    through torch's stream pool, and the caching allocator keeps free blocks per stream: temporaries of one
+    call could not be reused by the next, which then pays cudaMalloc (sporadic 20-300 ms) instead."""
+    import torch
+    key = (torch.device(device).index, kind)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 def check(rc, what=""):
     global LAUNCHES
     LAUNCHES += 1

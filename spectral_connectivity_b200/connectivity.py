@@ -317,7 +317,7 @@ class Connectivity:
         # next chunk computes
         host, copy_stream = {}, None
         if self._output == "numpy":
-            copy_stream = torch.cuda.Stream(device=dev)
+            copy_stream = _lib.side_stream(dev, "d2h")
             for name, t in out.items():
                 shp = (t.shape[0], fnn) + tuple(t.shape[2:])
                 host[name] = torch.empty(shp, dtype=t.dtype, pin_memory=True)

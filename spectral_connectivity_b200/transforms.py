@@ -168,7 +168,7 @@ class Multitaper:
         self.time_series = torch.empty(tuple(ts.shape), dtype=torch.float32, device=dev)
         self._finite_flag = torch.ones((), dtype=torch.bool, device=dev)
         self._h2d_events = []
-        copy_stream = torch.cuda.Stream(device=dev)
+        copy_stream = _lib.side_stream(dev, "h2d")
         copy_stream.wait_stream(torch.cuda.current_stream(dev))
         rows = max(1, -(-n_rows // n_slabs))
         with torch.cuda.stream(copy_stream):
