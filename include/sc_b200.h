@@ -151,10 +151,12 @@ int sc_granger_pairwise(const void* csm_c64, const float* power, int64_t B, int 
                         int64_t workspace_bytes, void* stream);
 int64_t sc_wilson_workspace_bytes(int nfft);
 
-/* minimum_phase_decomposition for S x S matrices, 1 <= S <= 32 (minimum_phase_decomposition.py:227-322):
+/* minimum_phase_decomposition for S x S matrices, 1 <= S <= 1024 (minimum_phase_decomposition.py:227-322):
  * csm c128 [B][F][S][S] -> G c128 same shape; F = nfft (two-sided) or nfft/2+1 with hermitian_half=1
- * (real time series).  One iteration = three stream-ordered kernels over the batch; convergence state
+ * (real time series).  One iteration = a few stream-ordered kernels over the batch; convergence state
  * lives on the device (no host synchronisation), every b converges independently (:310-315).
+ * S <= 32: one warp per (b, f) matrix in shared memory.  S > 32 (BASELINE config 5: 512 channels): blocked
+ * in-place Gauss-Jordan inversion with partial pivoting + tiled c128 GEMMs in global memory.
  * workspace: sc_wilson_general_workspace_bytes(B, F, S). */
 int sc_wilson(const void* csm_c128, int64_t B, int F, int nfft, int hermitian_half, int S, double tolerance,
               int max_iterations, const void* twiddle_c128, void* out_g_c128, int* out_iters, int* out_flags,
@@ -166,17 +168,22 @@ int64_t sc_wilson_general_workspace_bytes(int64_t B, int F, int S);
  *  sc_mvar_transfer  H = G (H0 + lambda I)^-1 for the first n_freq_out bins (c128 [B][n_freq_out][S][S]) and
  *                    the noise covariance H0 H0^T (f64 [B][S][S], may be NULL); lambda is the caller's
  *                    Tikhonov term 1e-12 * mean(H0^2) over all windows (:1742-1746)
- *  sc_mvar_inverse   A = (H + lambda I)^-1 per (b, f): the MVAR Fourier coefficients (:580-588) */
+ *  sc_mvar_inverse   A = (H + lambda I)^-1 per (b, f): the MVAR Fourier coefficients (:580-588)
+ * workspace (S > 32 only, else NULL/0): sc_mvar_workspace_bytes(B, 2, S) for sc_mvar_transfer,
+ * sc_mvar_workspace_bytes(BF, 1, S) for sc_mvar_inverse. */
 int sc_mvar_lag0(const void* g_c128, int64_t B, int F, int nfft, int hermitian_half, int S, double* out_h0,
                  void* stream);
 int sc_mvar_transfer(const void* g_c128, const double* h0, double lambda, int64_t B, int F, int n_freq_out, int S,
-                     void* out_h_c128, double* out_sigma, void* stream);
-int sc_mvar_inverse(const void* h_c128, double lambda, int64_t BF, int S, void* out_a_c128, void* stream);
+                     void* out_h_c128, double* out_sigma, void* workspace, int64_t workspace_bytes, void* stream);
+int sc_mvar_inverse(const void* h_c128, double lambda, int64_t BF, int S, void* out_a_c128, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+int64_t sc_mvar_workspace_bytes(int64_t B, int F, int S);
 
 /* directed_transfer_function (0), directed_coherence (1), partial_directed_coherence (2),
  * generalized_partial_directed_coherence (3), direct_directed_transfer_function (4)
  * (connectivity.py:1237-1426): f32 [B][F][S][S] from H and/or A (c128 [B][F][S][S]) and the noise
- * covariance (f64 [B][S][S]); scratch: B*S doubles (measure 4 only). */
+ * covariance (f64 [B][S][S]); scratch: B*S doubles (measure 4 only) for S <= 32, B*S + 2*B*F*S doubles
+ * (every measure) for S > 32. */
 int sc_mvar_measure(int measure, const void* h_c128, const void* a_c128, const double* sigma, int64_t B, int F, int S,
                     double* scratch, float* out, void* stream);
 

@@ -548,37 +548,38 @@ class Connectivity:
         raise NotImplementedError  # connectivity.py:1221-1224
 
     # ---- MVAR family from the full-matrix Wilson factor ----------
-    _MVAR_MAX_SIGNALS = 32
+    _MVAR_MAX_SIGNALS = 1024
+    _MVAR_CACHE_BYTES = 48 << 30  # above this the factor is not cached: measures stream over window chunks
 
-    def _mvar(self, tolerance=1e-8, max_iterations=60):
-        """Factor the expected CSM once and cache H (non-negative bins), the noise covariance and the
-        MVAR Fourier coefficients (the reference re-runs Wilson on every property access,
-        connectivity.py:567-588)."""
-        if getattr(self, "_mvar_cache", None) is not None:
-            return self._mvar_cache
+    def _mvar_check(self):
         if self.expectation_type not in _GRANGER_OK:
             raise NotImplementedError(
                 f"MVAR measures with expectation_type='{self.expectation_type}' couple the Wilson convergence test "
                 "across a kept axis; only " + ", ".join(_GRANGER_OK) + " are supported.")
-        lib = _lib.load()
-        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        n_sig = self._shape[4]
         if n_sig > self._MVAR_MAX_SIGNALS:
             raise NotImplementedError(
                 f"full-matrix Wilson factorisation on the device handles up to {self._MVAR_MAX_SIGNALS} signals "
                 f"(got {n_sig}); use pairwise_spectral_granger_prediction or a signal subset")
-        fnn = nfft // 2 + 1
-        herm = 1 if self._hermitian else 0
-        n_freq = fnn if self._hermitian else nfft
-        dev = self._device
+
+    def _mvar_bytes(self):
+        """Device bytes of the cached path: CSM, G, H, A and the Wilson workspace for every kept index."""
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
         kept = self._kept_dims()
         n_batch = int(np.prod(kept)) if kept else 1
-        scale = 1.0 / self.n_observations
+        n_freq = nfft // 2 + 1 if self._hermitian else nfft
+        return 8 * n_batch * n_freq * n_sig * n_sig * 16
+
+    def _mvar_from_csm(self, csm, tolerance, max_iterations):
+        """Expected CSM c64 [b][n_freq][S][S] -> dict(g, h, sigma, a, iters, flags) (connectivity.py:567-588,
+        1679-1748).  The Tikhonov terms use the mean over the batch passed in."""
+        lib = _lib.load()
+        nfft, n_sig = self._shape[3], self._shape[4]
+        fnn = nfft // 2 + 1
+        herm = 1 if self._hermitian else 0
+        n_batch, n_freq = csm.shape[0], csm.shape[1]
+        dev = self._device
         st = _lib.stream_ptr()
-        csm = torch.empty((n_batch, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
-        for b0, b1, xp, nr in self._chunks(n_freq):
-            _lib.check(lib.sc_csm(_lib.ptr(xp), b1 - b0, n_freq, nr, n_sig, scale, _lib.CSM_CROSS,
-                                  _lib.ptr(csm[b0:b1]), st), "sc_csm")
-            self._allreduce(csm[b0:b1])
         csm = csm.to(torch.complex128)
         g = torch.empty_like(csm)
         iters = torch.zeros(n_batch, dtype=torch.int32, device=dev)
@@ -589,34 +590,112 @@ class Connectivity:
         _lib.check(lib.sc_wilson(_lib.ptr(csm), n_batch, n_freq, nfft, herm, n_sig, float(tolerance), int(max_iterations),
                                  _lib.ptr(tw), _lib.ptr(g), _lib.ptr(iters), _lib.ptr(flags), _lib.ptr(ws), ws_bytes, st),
                    "sc_wilson")
-        n_bad = int((flags & _lib.FLAG_NOT_CONVERGED).ne(0).sum())
-        if n_bad:
-            logger.warning(f"Maximum iterations reached. {n_batch - n_bad} of {n_batch} converged")
-        if int((flags & _lib.FLAG_NOT_SPD).ne(0).sum()):
-            logger.warning("Computing the initial conditions using the Cholesky failed; those factors are NaN.")
+        del csm
         h0 = torch.empty((n_batch, n_sig, n_sig), dtype=torch.float64, device=dev)
         _lib.check(lib.sc_mvar_lag0(_lib.ptr(g), n_batch, n_freq, nfft, herm, n_sig, _lib.ptr(h0), st), "sc_mvar_lag0")
         lam = TIKHONOV_REGULARIZATION_FACTOR * float((h0 * h0).mean())  # over all windows, connectivity.py:1742-1746
         h = torch.empty((n_batch, fnn, n_sig, n_sig), dtype=torch.complex128, device=dev)
         sigma = torch.empty((n_batch, n_sig, n_sig), dtype=torch.float64, device=dev)
+        need = max(lib.sc_mvar_workspace_bytes(n_batch, 2, n_sig), lib.sc_mvar_workspace_bytes(n_batch * fnn, 1, n_sig))
+        if need > ws_bytes:
+            del ws
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            ws_bytes = need
         _lib.check(lib.sc_mvar_transfer(_lib.ptr(g), _lib.ptr(h0), lam, n_batch, n_freq, fnn, n_sig, _lib.ptr(h),
-                                        _lib.ptr(sigma), st), "sc_mvar_transfer")
+                                        _lib.ptr(sigma), _lib.ptr(ws), ws_bytes, st), "sc_mvar_transfer")
         lam_a = TIKHONOV_REGULARIZATION_FACTOR * float((h.real ** 2 + h.imag ** 2).mean())  # connectivity.py:585
         a = torch.empty_like(h)
-        _lib.check(lib.sc_mvar_inverse(_lib.ptr(h), lam_a, n_batch * fnn, n_sig, _lib.ptr(a), st), "sc_mvar_inverse")
-        self.last_wilson_iterations, self.last_wilson_flags = iters, flags
-        self._mvar_cache = dict(g=g, h=h, sigma=sigma, a=a, kept=kept, n_batch=n_batch, fnn=fnn, n_sig=n_sig)
-        return self._mvar_cache
+        _lib.check(lib.sc_mvar_inverse(_lib.ptr(h), lam_a, n_batch * fnn, n_sig, _lib.ptr(a), _lib.ptr(ws), ws_bytes, st),
+                   "sc_mvar_inverse")
+        return dict(g=g, h=h, sigma=sigma, a=a, iters=iters, flags=flags, n_batch=n_batch, fnn=fnn, n_sig=n_sig)
 
-    def _mvar_measure(self, code):
+    def _mvar_warn(self, flags):
+        n_batch = flags.numel()
+        n_bad = int((flags & _lib.FLAG_NOT_CONVERGED).ne(0).sum())
+        if n_bad:
+            logger.warning(f"Maximum iterations reached. {n_batch - n_bad} of {n_batch} converged")
+        if int((flags & _lib.FLAG_NOT_SPD).ne(0).sum()):
+            logger.warning("Computing the initial conditions using the Cholesky failed; those factors are NaN.")
+
+    def _mvar(self, tolerance=1e-8, max_iterations=60):
+        """Factor the expected CSM once and cache H (non-negative bins), the noise covariance and the
+        MVAR Fourier coefficients (the reference re-runs Wilson on every property access,
+        connectivity.py:567-588)."""
+        if getattr(self, "_mvar_cache", None) is not None:
+            return self._mvar_cache
+        self._mvar_check()
         lib = _lib.load()
-        m = self._mvar()
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        n_freq = nfft // 2 + 1 if self._hermitian else nfft
+        kept = self._kept_dims()
+        n_batch = int(np.prod(kept)) if kept else 1
+        scale = 1.0 / self.n_observations
+        st = _lib.stream_ptr()
+        csm = torch.empty((n_batch, n_freq, n_sig, n_sig), dtype=torch.complex64, device=self._device)
+        for b0, b1, xp, nr in self._chunks(n_freq):
+            _lib.check(lib.sc_csm(_lib.ptr(xp), b1 - b0, n_freq, nr, n_sig, scale, _lib.CSM_CROSS,
+                                  _lib.ptr(csm[b0:b1]), st), "sc_csm")
+            self._allreduce(csm[b0:b1])
+        m = self._mvar_from_csm(csm, tolerance, max_iterations)
+        self._mvar_warn(m["flags"])
+        self.last_wilson_iterations, self.last_wilson_flags = m["iters"], m["flags"]
+        m["kept"] = kept
+        self._mvar_cache = m
+        return m
+
+    def _mvar_measure_of(self, m, code):
+        lib = _lib.load()
         nb, fnn, n_sig = m["n_batch"], m["fnn"], m["n_sig"]
         out = torch.empty((nb, fnn, n_sig, n_sig), dtype=torch.float32, device=self._device)
-        scratch = torch.empty((nb, n_sig), dtype=torch.float64, device=self._device)
+        n_scratch = nb * n_sig + (2 * nb * fnn * n_sig if n_sig > 32 else 0)
+        scratch = torch.empty(n_scratch, dtype=torch.float64, device=self._device)
         _lib.check(lib.sc_mvar_measure(code, _lib.ptr(m["h"]), _lib.ptr(m["a"]), _lib.ptr(m["sigma"]), nb, fnn, n_sig,
                                        _lib.ptr(scratch), _lib.ptr(out), _lib.stream_ptr()), "sc_mvar_measure")
-        return self._finish(out.reshape(m["kept"] + (fnn, n_sig, n_sig)))
+        return out
+
+    def _mvar_measure(self, code, tolerance=1e-8, max_iterations=60):
+        if getattr(self, "_mvar_cache", None) is not None or self._mvar_bytes() <= self._MVAR_CACHE_BYTES:
+            m = self._mvar(tolerance, max_iterations)
+            out = self._mvar_measure_of(m, code)
+            return self._finish(out.reshape(m["kept"] + tuple(out.shape[1:])))
+        # Too large to keep the factor of every window (BASELINE config 5: 256 GB): stream window chunks,
+        # factor + measure per chunk, keep only the result.  The 1e-12-relative Tikhonov terms then use the
+        # chunk mean instead of the mean over all windows (a 1e-12-relative change).
+        self._mvar_check()
+        lib = _lib.load()
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        n_freq = nfft // 2 + 1 if self._hermitian else nfft
+        fnn = nfft // 2 + 1
+        kept = self._kept_dims()
+        n_batch = int(np.prod(kept)) if kept else 1
+        scale = 1.0 / self.n_observations
+        st = _lib.stream_ptr()
+        to_host = self._output != "torch"
+        result = (torch.empty((n_batch, fnn, n_sig, n_sig), dtype=torch.float32, pin_memory=True) if to_host else
+                  torch.empty((n_batch, fnn, n_sig, n_sig), dtype=torch.float32, device=self._device))
+        all_iters = torch.zeros(n_batch, dtype=torch.int32, device=self._device)
+        all_flags = torch.zeros(n_batch, dtype=torch.int32, device=self._device)
+        per_item = 8 * n_freq * n_sig * n_sig * 16
+        sub = max(1, self._MVAR_CACHE_BYTES // per_item)
+        for b0, b1, xp, nr in self._chunks(n_freq):
+            csm = torch.empty((b1 - b0, n_freq, n_sig, n_sig), dtype=torch.complex64, device=self._device)
+            _lib.check(lib.sc_csm(_lib.ptr(xp), b1 - b0, n_freq, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(csm), st),
+                       "sc_csm")
+            self._allreduce(csm)
+            del xp
+            for c0 in range(0, b1 - b0, sub):
+                c1 = min(b1 - b0, c0 + sub)
+                m = self._mvar_from_csm(csm[c0:c1], tolerance, max_iterations)
+                out = self._mvar_measure_of(m, code)
+                all_iters[b0 + c0:b0 + c1] = m["iters"]
+                all_flags[b0 + c0:b0 + c1] = m["flags"]
+                result[b0 + c0:b0 + c1].copy_(out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                del m, out
+        self._mvar_warn(all_flags)
+        self.last_wilson_iterations, self.last_wilson_flags = all_iters, all_flags
+        result = result.reshape(kept + (fnn, n_sig, n_sig))
+        return result.numpy() if to_host else result
 
     @property
     def _minimum_phase_factor(self):

@@ -226,6 +226,83 @@ __global__ void epilogue_kernel(int measure, const float* __restrict__ in0, cons
     }
 }
 
+// Coherence family (coherency / |coherency|^2 / phase / imaginary coherence) for S % 4 == 0: HBM-bound, 8 B in +
+// 4 (or 8) B out per pair-frequency.  One thread owns 4 consecutive columns of one matrix row (two 16-byte
+// CSM loads, one 16-byte store) and ROWS rows are in flight per thread to cover the DRAM latency.
+template <int ROWS>
+__global__ void __launch_bounds__(256) coherence_epilogue_vec_kernel(int measure, const float4* __restrict__ csm,
+                                                                      const float* __restrict__ power, long long n_rows,
+                                                                      int S, float* __restrict__ out) {
+    const float qnan = __int_as_float(0x7fc00000);
+    const int q_per_row = S >> 2;                       // 4-column groups per row
+    const int rows_per_cta = 256 / q_per_row > 0 ? 256 / q_per_row : 1;
+    const int active = rows_per_cta * q_per_row;        // threads with work (all 256 when S | 1024)
+    if ((int)threadIdx.x >= active && q_per_row <= 256) return;
+    const int rl = threadIdx.x / q_per_row;             // row within the CTA's group
+    for (long long base = (long long)blockIdx.x * rows_per_cta * ROWS; base < n_rows;
+         base += (long long)gridDim.x * rows_per_cta * ROWS) {
+        for (int q0 = threadIdx.x % q_per_row; q0 < q_per_row; q0 += 256) {  // S > 1024: several groups per thread
+            float4 a[ROWS], b[ROWS];
+            long long row[ROWS];
+#pragma unroll
+            for (int u = 0; u < ROWS; ++u) {
+                row[u] = base + (long long)u * rows_per_cta + rl;
+                if (row[u] < n_rows) {
+                    const float4* src = csm + (row[u] * S + 4 * q0) / 2;
+                    a[u] = __ldcs(src);
+                    b[u] = __ldcs(src + 1);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < ROWS; ++u) {
+                if (row[u] >= n_rows) continue;
+                const long long bf = row[u] / S;
+                const int i = (int)(row[u] - bf * S);
+                const float pi = sqrtf(power[bf * S + i]);
+                const float4 pj = *reinterpret_cast<const float4*>(power + bf * S + 4 * q0);
+                const float re[4] = {a[u].x, a[u].z, b[u].x, b[u].z}, im[4] = {a[u].y, a[u].w, b[u].y, b[u].w};
+                const float pjs[4] = {pj.x, pj.y, pj.z, pj.w};
+                float r4[4], i4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float norm = pi * sqrtf(pjs[e]);
+                    norm = norm < (float)kEps64 ? (float)kEps64 : norm;  // connectivity.py:649-652
+                    const float inv = 1.0f / norm;
+                    r4[e] = re[e] * inv;
+                    i4[e] = im[e] * inv;
+                }
+                const int j0 = 4 * q0;
+                if (measure == SC_M_COHERENCY) {
+                    float4 o0 = make_float4(r4[0], i4[0], r4[1], i4[1]), o1 = make_float4(r4[2], i4[2], r4[3], i4[3]);
+                    if (i == j0) o0.x = o0.y = qnan;
+                    if (i == j0 + 1) o0.z = o0.w = qnan;
+                    if (i == j0 + 2) o1.x = o1.y = qnan;
+                    if (i == j0 + 3) o1.z = o1.w = qnan;
+                    float4* dst = reinterpret_cast<float4*>(out) + (row[u] * S + j0) / 2;
+                    __stcs(dst, o0);
+                    __stcs(dst + 1, o1);
+                } else {
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (measure == SC_M_COHERENCE_MAG) {
+                            float m = fmaf(r4[e], r4[e], i4[e] * i4[e]);
+                            m = m < 0.f ? 0.f : (m > 1.f ? 1.f : m);  // np.clip semantics: NaN stays NaN
+                            o[e] = (i == j0 + e) ? qnan : m;
+                        } else if (measure == SC_M_COHERENCE_PHASE) {
+                            o[e] = (i == j0 + e) ? qnan : atan2f(i4[e], r4[e]);
+                        } else {
+                            const float m = fabsf(i4[e]);
+                            o[e] = m > 1.f ? 1.f : m;
+                        }
+                    }
+                    __stcs(reinterpret_cast<float4*>(out + row[u] * S + j0), make_float4(o[0], o[1], o[2], o[3]));
+                }
+            }
+        }
+    }
+}
+
 unsigned grid_for(long long total, int threads) {
     long long blocks = (total + threads - 1) / threads;
     const long long cap = (long long)sc_num_sms() * 32;
@@ -282,6 +359,17 @@ extern "C" int sc_pairwise_epilogue(int measure, const void* in0, const float* i
     SC_CHECK_ARG(measure > SC_M_IMAG_COHERENCE || in1, "sc_pairwise_epilogue: measure %d needs the power array", measure);
     SC_CHECK_ARG(B > 0 && F > 0 && S > 0, "sc_pairwise_epilogue: non-positive size");
     const long long rows = B * F * S;
+    if (measure <= SC_M_IMAG_COHERENCE && S % 4 == 0 && S <= 1024 && 1024 % S == 0) {
+        constexpr int kRows = 4;
+        const int rows_per_cta = (int)(1024 / S);
+        const long long ctas = (rows + (long long)rows_per_cta * kRows - 1) / ((long long)rows_per_cta * kRows);
+        const long long cap_v = (long long)sc_num_sms() * 16;
+        coherence_epilogue_vec_kernel<kRows><<<(unsigned)(ctas < cap_v ? ctas : cap_v), 256, 0,
+                                               reinterpret_cast<cudaStream_t>(stream)>>>(
+            measure, reinterpret_cast<const float4*>(in0), in1, rows, (int)S, reinterpret_cast<float*>(out));
+        SC_LAUNCH_OK();
+        return SC_OK;
+    }
     const int threads = S >= 256 ? 256 : (S >= 128 ? 128 : (S >= 64 ? 64 : 32));
     const long long cap = (long long)sc_num_sms() * 64;
     epilogue_kernel<<<(unsigned)(rows < cap ? rows : cap), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(

@@ -432,11 +432,82 @@ __global__ void mvar_measure_kernel(int measure, const cd* h, const cd* a, const
     }
 }
 
+#include "wilson_blocked.cuh"
+
+constexpr int kMaxBigS = 1024;
+
 int check_s(int S, const char* what) {
-    if (S < 1 || S > kMaxS) {
-        sc_set_error("%s: S=%d outside [1, %d] (larger matrices need the blocked solver, next round)", what, S, kMaxS);
+    if (S < 1 || S > kMaxBigS) {
+        sc_set_error("%s: S=%d outside [1, %d]", what, S, kMaxBigS);
         return SC_ERR_UNSUPPORTED;
     }
+    return SC_OK;
+}
+
+inline unsigned grid_for(long long n, int threads) {
+    const long long g = (n + threads - 1) / threads;
+    const long long cap = (long long)sc_num_sms() * 32;
+    return (unsigned)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+// Wilson iteration for S > kMaxS (see wilson_blocked.cuh).  Workspace: 3 matrix buffers + inversion scratch.
+int wilson_blocked(WgParams p, int max_iterations, cd* out_g, int* out_iters, int* out_flags, unsigned char* ws,
+                   cudaStream_t st) {
+    const int S = p.S, F = p.F;
+    const long long B = p.B, count = B * F;
+    const size_t mat = (size_t)count * S * S;
+    cd* w0 = reinterpret_cast<cd*>(ws);
+    cd* w1 = w0 + mat;
+    cd* w2 = w1 + mat;
+    unsigned char* tail = reinterpret_cast<unsigned char*>(w2 + mat);
+    p.err = reinterpret_cast<double*>(tail);
+    p.state = reinterpret_cast<int*>(tail + (size_t)B * 8);
+    p.iters = reinterpret_cast<int*>(tail + (size_t)B * 16);
+    double* lag0 = reinterpret_cast<double*>(tail + (((size_t)B * 32 + 255) / 256) * 256);
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(lag0) + (((size_t)B * S * S * 8 + 255) / 256) * 256;
+    const size_t plus_smem = (size_t)3 * p.nfft * sizeof(cd);
+    if (plus_smem > 48 * 1024)
+        SC_CUDA_OK(cudaFuncSetAttribute(wg_plus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plus_smem));
+    // lag-0 covariance -> Cholesky -> G0 = L^T for every frequency
+    mvar_lag0_kernel<<<(unsigned)B, 256, 0, st>>>(p.csm, B, F, p.nfft, p.herm, S, lag0);
+    zb_cholesky_kernel<<<(unsigned)B, 1024, (size_t)S * sizeof(double), st>>>(lag0, S, p.state, p.iters, p.err);
+    cd* gcur = out_g;
+    cd* free_a = w0;
+    cd* free_b = w1;
+    cd* bp = w2;
+    zb_init_g_kernel<<<dim3(grid_for((long long)F * S * S, 256), (unsigned)B), 256, 0, st>>>(lag0, p.state, F, S, gcur);
+    SC_LAUNCH_OK();
+    const long long SS = (long long)S * S;
+    const int n_entries = p.herm ? S * (S + 1) / 2 : S * S;
+    for (int it = 0; it < max_iterations; ++it) {
+        // Ginv: copy G, invert in place, unscramble into free_b
+        SC_CUDA_OK(cudaMemcpyAsync(free_a, gcur, mat * sizeof(cd), cudaMemcpyDeviceToDevice, st));
+        if (int rc = zb_inverse(free_a, free_b, count, S, p.state, F, nullptr, scratch, st)) return rc;
+        ZGemmParams g;
+        g.n_inner = F; g.S = S; g.state = p.state; g.passthrough = 0; g.err = nullptr;
+        g.a_so = g.b_so = g.c_so = (long long)F * SS;
+        g.a_si = g.b_si = g.c_si = SS;
+        // T = Ginv S -> free_a
+        g.A = free_b; g.Bm = p.csm; g.C = free_a; g.conj_b = 0; g.add_identity = 0;
+        zb_gemm(g, count, st);
+        // B = T Ginv^H + I -> bp
+        g.A = free_a; g.Bm = free_b; g.C = bp; g.conj_b = 1; g.add_identity = 1;
+        zb_gemm(g, count, st);
+        p.bp = bp;
+        wg_plus_kernel<<<dim3(n_entries, (unsigned)B), kThreads, plus_smem, st>>>(p);
+        // G <- G P -> free_a, max |dG| per window; converged windows are copied through
+        g.A = gcur; g.Bm = bp; g.C = free_a; g.conj_b = 0; g.add_identity = 0; g.passthrough = 1; g.err = p.err;
+        zb_gemm(g, count, st);
+        wg_check_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(p);
+        SC_LAUNCH_OK();
+        cd* t = gcur;
+        gcur = free_a;
+        free_a = t;
+    }
+    if (gcur != out_g) SC_CUDA_OK(cudaMemcpyAsync(out_g, gcur, mat * sizeof(cd), cudaMemcpyDeviceToDevice, st));
+    if (out_flags) wg_finish_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(p.state, out_flags, B);
+    if (out_iters) SC_CUDA_OK(cudaMemcpyAsync(out_iters, p.iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    SC_LAUNCH_OK();
     return SC_OK;
 }
 
@@ -444,7 +515,15 @@ int check_s(int S, const char* what) {
 
 extern "C" int64_t sc_wilson_general_workspace_bytes(int64_t B, int F, int S) {
     if (B < 1 || F < 1 || S < 1) return 0;
-    return (int64_t)B * F * S * S * (int64_t)sizeof(cd) + (int64_t)B * 32;
+    const int64_t mat = (int64_t)B * F * S * S * (int64_t)sizeof(cd);
+    if (S <= kMaxS) return mat + (int64_t)B * 32;
+    return 3 * mat + (((int64_t)B * 32 + 255) / 256) * 256 + (((int64_t)B * S * S * 8 + 255) / 256) * 256 +
+           zb_inverse_scratch_bytes(B * F, S);
+}
+
+extern "C" int64_t sc_mvar_workspace_bytes(int64_t B, int F, int S) {
+    if (B < 1 || F < 1 || S <= kMaxS) return 0;
+    return (int64_t)B * F * S * S * (int64_t)sizeof(cd) + zb_inverse_scratch_bytes(B * F, S) + 256;
 }
 
 extern "C" int sc_wilson(const void* csm_c128, int64_t B, int F, int nfft, int hermitian_half, int S, double tolerance,
@@ -480,6 +559,10 @@ extern "C" int sc_wilson(const void* csm_c128, int64_t B, int F, int nfft, int h
         sc_set_error("sc_wilson: nfft=%d needs %zu bytes of shared memory for the causal projection", nfft, plus_smem);
         return SC_ERR_UNSUPPORTED;
     }
+    SC_CHECK_ARG(B <= 65535, "sc_wilson: at most 65535 windows per call");
+    if (S > kMaxS)
+        return wilson_blocked(p, max_iterations, reinterpret_cast<cd*>(out_g_c128), out_iters, out_flags,
+                              reinterpret_cast<unsigned char*>(workspace), st);
     const size_t lp_per_warp = (size_t)(4 * SS + S) * sizeof(cd);
     int lp_wpb = (int)(((size_t)sc_max_smem_optin() - 2048) / lp_per_warp);
     lp_wpb = lp_wpb > 8 ? 8 : (lp_wpb < 1 ? 1 : lp_wpb);
@@ -497,7 +580,6 @@ extern "C" int sc_wilson(const void* csm_c128, int64_t B, int F, int nfft, int h
     const unsigned lp_grid = (unsigned)((items + lp_wpb - 1) / lp_wpb);
     const unsigned up_grid = (unsigned)((items + up_wpb - 1) / up_wpb);
     const int n_entries = hermitian_half ? S * (S + 1) / 2 : SS;
-    SC_CHECK_ARG(B <= 65535, "sc_wilson: at most 65535 windows per call");
     wg_init_kernel<<<(unsigned)B, 256, SS * sizeof(double), st>>>(p);
     SC_LAUNCH_OK();
     for (int it = 0; it < max_iterations; ++it) {
@@ -524,26 +606,66 @@ extern "C" int sc_mvar_lag0(const void* g_c128, int64_t B, int F, int nfft, int 
 }
 
 extern "C" int sc_mvar_transfer(const void* g_c128, const double* h0, double lambda, int64_t B, int F, int n_freq_out,
-                                int S, void* out_h_c128, double* out_sigma, void* stream) {
+                                int S, void* out_h_c128, double* out_sigma, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
     SC_CHECK_ARG(g_c128 && h0 && out_h_c128 && B > 0 && F > 0 && n_freq_out > 0 && n_freq_out <= F,
                  "sc_mvar_transfer: bad argument");
     if (int rc = check_s(S, "sc_mvar_transfer")) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (S > kMaxS) {
+        const int64_t need = sc_mvar_workspace_bytes(B, 2, S);  // (H0 + lambda I) and its inverse: 2 matrices per window
+        if (!workspace || workspace_bytes < need) {
+            sc_set_error("sc_mvar_transfer: workspace of %lld bytes required, got %lld", (long long)need,
+                         (long long)workspace_bytes);
+            return SC_ERR_WORKSPACE;
+        }
+        const long long SS = (long long)S * S;
+        cd* work = reinterpret_cast<cd*>(workspace);
+        cd* minv = work + (size_t)B * SS;
+        unsigned char* scratch = reinterpret_cast<unsigned char*>(minv + (size_t)B * SS);
+        zb_shift_copy_kernel<<<grid_for(B * SS, 256), 256, 0, st>>>(nullptr, h0, lambda, B, S, work);
+        if (int rc = zb_inverse(work, minv, B, S, nullptr, 1, nullptr, scratch, st)) return rc;
+        ZGemmParams g;
+        g.A = reinterpret_cast<const cd*>(g_c128); g.Bm = minv; g.C = reinterpret_cast<cd*>(out_h_c128);
+        g.a_so = (long long)F * SS; g.a_si = SS; g.b_so = SS; g.b_si = 0; g.c_so = (long long)n_freq_out * SS; g.c_si = SS;
+        g.n_inner = n_freq_out; g.S = S; g.conj_b = 0; g.add_identity = 0; g.state = nullptr; g.passthrough = 0;
+        g.err = nullptr;
+        zb_gemm(g, B * n_freq_out, st);
+        if (out_sigma) zb_sigma_kernel<<<grid_for(B * SS, 256), 256, 0, st>>>(h0, B, S, out_sigma);
+        SC_LAUNCH_OK();
+        return SC_OK;
+    }
     const size_t smem = (size_t)(2 * S * S + S) * sizeof(cd);
-    mvar_transfer_kernel<<<(unsigned)B, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const cd*>(g_c128), h0, lambda, F, n_freq_out, S, reinterpret_cast<cd*>(out_h_c128), out_sigma);
+    mvar_transfer_kernel<<<(unsigned)B, 256, smem, st>>>(reinterpret_cast<const cd*>(g_c128), h0, lambda, F, n_freq_out, S,
+                                                          reinterpret_cast<cd*>(out_h_c128), out_sigma);
     SC_LAUNCH_OK();
     return SC_OK;
 }
 
-extern "C" int sc_mvar_inverse(const void* h_c128, double lambda, int64_t BF, int S, void* out_a_c128, void* stream) {
+extern "C" int sc_mvar_inverse(const void* h_c128, double lambda, int64_t BF, int S, void* out_a_c128, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
     SC_CHECK_ARG(h_c128 && out_a_c128 && BF > 0, "sc_mvar_inverse: bad argument");
     if (int rc = check_s(S, "sc_mvar_inverse")) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (S > kMaxS) {
+        const int64_t need = sc_mvar_workspace_bytes(BF, 1, S);
+        if (!workspace || workspace_bytes < need) {
+            sc_set_error("sc_mvar_inverse: workspace of %lld bytes required, got %lld", (long long)need,
+                         (long long)workspace_bytes);
+            return SC_ERR_WORKSPACE;
+        }
+        cd* work = reinterpret_cast<cd*>(workspace);
+        unsigned char* scratch = reinterpret_cast<unsigned char*>(work + (size_t)BF * S * S);
+        zb_shift_copy_kernel<<<grid_for(BF * (long long)S * S, 256), 256, 0, st>>>(reinterpret_cast<const cd*>(h_c128), nullptr,
+                                                                                  lambda, BF, S, work);
+        return zb_inverse(work, reinterpret_cast<cd*>(out_a_c128), BF, S, nullptr, 1, nullptr, scratch, st);
+    }
     const size_t per_warp = (size_t)(2 * S * S + S) * sizeof(cd);
     int wpb = (int)(((size_t)sc_max_smem_optin() - 2048) / per_warp);
     wpb = wpb > 8 ? 8 : (wpb < 1 ? 1 : wpb);
     if (per_warp * wpb > 48 * 1024)
         SC_CUDA_OK(cudaFuncSetAttribute(mvar_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));
-    mvar_inverse_kernel<<<(unsigned)((BF + wpb - 1) / wpb), wpb * 32, per_warp * wpb, reinterpret_cast<cudaStream_t>(stream)>>>(
+    mvar_inverse_kernel<<<(unsigned)((BF + wpb - 1) / wpb), wpb * 32, per_warp * wpb, st>>>(
         reinterpret_cast<const cd*>(h_c128), lambda, BF, S, reinterpret_cast<cd*>(out_a_c128));
     SC_LAUNCH_OK();
     return SC_OK;
@@ -562,6 +684,20 @@ extern "C" int sc_mvar_measure(int measure, const void* h_c128, const void* a_c1
     if (measure == 4) {
         mvar_inflow_all_kernel<<<(unsigned)B, 64, 0, st>>>(reinterpret_cast<const cd*>(h_c128), F, S, scratch);
         SC_LAUNCH_OK();
+    }
+    if (S > kMaxS) {
+        SC_CHECK_ARG(scratch, "sc_mvar_measure: S > %d needs a scratch of B*S + 2*B*F*S doubles", kMaxS);
+        double* rs = scratch + (size_t)B * S;
+        double* cs = rs + (size_t)B * F * S;
+        const cd* h = reinterpret_cast<const cd*>(h_c128);
+        const cd* a = reinterpret_cast<const cd*>(a_c128);
+        const bool need_h = measure == 0 || measure == 1 || measure == 4, need_a = measure >= 2;
+        zb_mvar_sums_kernel<<<(unsigned)(B * F), 256, 0, st>>>(measure, need_h ? h : nullptr, need_a ? a : nullptr, sigma, F, S,
+                                                              rs, cs);
+        zb_mvar_measure_kernel<<<grid_for(B * F * (long long)S * S, 256), 256, 0, st>>>(
+            measure, need_h ? h : nullptr, need_a ? a : nullptr, sigma, scratch, rs, cs, B * F, F, S, out);
+        SC_LAUNCH_OK();
+        return SC_OK;
     }
     const size_t smem = (size_t)(2 * S * S + 2 * S) * sizeof(double);
     mvar_measure_kernel<<<(unsigned)(B * F), 128, smem, st>>>(measure, reinterpret_cast<const cd*>(h_c128),

@@ -24,8 +24,8 @@ def minimum_phase_decomposition(cross_spectral_matrix, tolerance=1e-8, max_itera
     tensor for torch input); with ``return_info`` also (iterations, flags) int32 arrays.
 
     2x2 matrices (the pairwise-Granger case) use the fused single-kernel path (``sc_wilson2``);
-    S x S matrices up to S = 32 use the batched multi-kernel path (``sc_wilson``); larger matrices
-    raise NotImplementedError.
+    S x S matrices up to S = 32 use the batched warp-per-matrix path and larger ones (up to 1024) the blocked
+    Gauss-Jordan / tiled-GEMM path (both ``sc_wilson``).
     """
     lib = _lib.load()
     is_torch = isinstance(cross_spectral_matrix, torch.Tensor)
@@ -36,8 +36,8 @@ def minimum_phase_decomposition(cross_spectral_matrix, tolerance=1e-8, max_itera
     n_sig = csm.shape[-1]
     if csm.shape[-2] != n_sig:
         raise ValueError("cross_spectral_matrix must be square in its last two dimensions")
-    if n_sig > 32:
-        raise NotImplementedError("device Wilson factorisation currently handles up to 32 x 32 matrices")
+    if n_sig > 1024:
+        raise NotImplementedError("device Wilson factorisation handles up to 1024 x 1024 matrices")
     if not torch.cuda.is_available():
         raise RuntimeError("spectral_connectivity_b200 needs a CUDA device; there is no CPU fallback.")
     dev = torch.device("cuda", torch.cuda.current_device())

@@ -450,7 +450,7 @@ def test_mvar_ranges_larger_system(sc):
     h, _ = O.mvar_transfer_function(O.expected_csm(coef, row_block=4))
     assert_parity(dtf, O.directed_transfer_function(h), TOL, "DTF vs oracle S=12")
     with pytest.raises(NotImplementedError):
-        big = sc.Connectivity(np.zeros((1, 2, 1, 8, 40), dtype=complex))
+        big = sc.Connectivity(np.zeros((1, 1, 1, 2, 1025), dtype=complex))
         big.directed_transfer_function()
 
 
