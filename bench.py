@@ -33,11 +33,14 @@ WORKLOADS = {
     "cfg3": dict(N=30_000, T=32, S=128, fs=1000.0, NW=4.0, duration=1.0),
     "cfg2": dict(N=10_000, T=16, S=64, fs=1000.0, NW=3.0, duration=1.0),
     "cfg1": dict(N=1000, T=4, S=8, fs=500.0, NW=2.0, duration=None),
+    # SURVEY.md config 5 geometry (512 ch x 128 trials @ 2 kHz, 9 tapers, 60 ms windows) on 8 of its 1000 windows
+    "cfg5w8": dict(N=960, T=128, S=512, fs=2000.0, NW=5.0, duration=0.060),
 }
 MEASURES = ["coherence_magnitude", "pairwise_spectral_granger_prediction"]
 # the other BASELINE.json configs are parity-test cases; `--workload` can still time them
 WORKLOAD_MEASURES = {"cfg1": ["coherence_magnitude"], "cfg2": ["power", "coherency"],
-                     "cfg3": ["expectation_cross_spectral_matrix", "weighted_phase_lag_index"]}
+                     "cfg3": ["expectation_cross_spectral_matrix", "weighted_phase_lag_index"],
+                     "cfg5w8": ["canonical_coherence", "directed_transfer_function"]}
 METRIC = "channel-pair-freqs/sec (CSM+coherence+Granger)"
 FP64_PEAK_NOMINAL_TFLOPS = 37.0  # B200 FP64 vector, nominal (not in MEASURED_PEAKS.json)
 
@@ -132,8 +135,8 @@ def run_reference(args, wl_name, wl):
 
 def workload_config(wl_name, wl, n_gpus):
     n, n_win, nfft, fnn = geometry(wl)
-    return {"workload": f"BASELINE configs[{wl_name[3]}]{' (reduced windows)' if len(wl_name) > 4 else ''}: {wl['S']}-channel x {wl['T']}-trial x "
-                        f"{wl['N'] / wl['fs']:.0f} s @ {wl['fs']:.0f} Hz, {int(2 * wl['NW'] - 1)} tapers, "
+    return {"workload": f"BASELINE.json configs[{int(wl_name[3]) - 1}] (SURVEY.md config {wl_name[3]}){' (reduced windows)' if len(wl_name) > 4 else ''}: {wl['S']}-channel x {wl['T']}-trial x "
+                        f"{wl['N'] / wl['fs']:g} s @ {wl['fs']:.0f} Hz, {int(2 * wl['NW'] - 1)} tapers, "
                         f"{n_win} windows of {n} samples, nfft {nfft}; " + " + ".join(WORKLOAD_MEASURES.get(wl_name, MEASURES)) +
                         (" (Wilson tol 1e-8, <=60 it)" if wl_name not in WORKLOAD_MEASURES else ""),
             "per_gpu_recording": [wl["N"], wl["T"], wl["S"]], "pair_freqs_per_gpu_step": pair_freqs(wl),
@@ -228,10 +231,21 @@ def run_gpu(args, wl_name, wl):
     measures = WORKLOAD_MEASURES.get(wl_name, MEASURES)
     has_granger = "pairwise_spectral_granger_prediction" in measures
 
+    def run_measures(c):
+        fused = [name for name in measures if name in sc.connectivity.MEASURES]
+        out = c.compute(fused) if fused else {}
+        for name in measures:
+            if name == "canonical_coherence":      # 64-channel groups
+                out[name] = c.canonical_coherence(np.arange(wl["S"]) // 64)[0]
+            elif name not in fused:
+                with _lib.timed(name):
+                    out[name] = getattr(c, name)()
+        return out
+
     def step_device():
         m = sc.Multitaper(x_dev, **kw)
         c = sc.Connectivity.from_multitaper(m, output="torch")
-        out = c.compute(measures)
+        out = run_measures(c)
         return c, out
 
     def barrier():
@@ -295,7 +309,7 @@ def run_gpu(args, wl_name, wl):
     def step_e2e():
         m = sc.Multitaper(x_np, **kw)                      # H2D from pinned host memory
         cc = sc.Connectivity.from_multitaper(m)            # output="numpy": D2H of every result
-        return cc.compute(measures)
+        return run_measures(cc)
 
     e2e_steps = max(1, min(args.steps, 3))
     del c

@@ -117,6 +117,13 @@ int sc_csm_simt(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, flo
 int sc_pairwise_epilogue(int measure, const void* in0, const float* in1, int64_t B, int64_t F, int64_t S,
                          double n_observations, void* out, void* stream);
 
+/* phase_slope_index (connectivity.py:1587-1650, _inner_combination :1652-1676): for every (b, i, j)
+ * Im sum_{q1 < q2} conj(c[f_q1]) c[f_q2] over the n_selected bins freq_index[q] (int32, device; the host
+ * applies the reference's band-pass and independent-frequency subsampling) of the coherency c64
+ * [B][F][S][S] -> f32 [B][S][S] (NaN diagonal inherited from the coherency). */
+int sc_phase_slope_index(const void* coherency_c64, int64_t B, int64_t F, int64_t S, const int* freq_index,
+                         int n_selected, float* out, void* stream);
+
 /* minimum_phase_decomposition(csm, tolerance, max_iterations) -- minimum_phase_decomposition.py:227-322
  * for 2x2 matrices: csm c128 [B][nfft][2][2] two-sided -> G c128 same shape.  Each b is an
  * independent unit of convergence (frozen at its first iterate with max|dG| < tol, :310-315).

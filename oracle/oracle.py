@@ -317,6 +317,22 @@ def pairwise_phase_consistency(coef, expectation_type="trials_tapers", row_block
 
 # --------------------------------------------------------------------------- #
 # Wilson spectral factorisation
+def phase_slope_index(coef, freqs, frequencies_of_interest=None, frequency_resolution=None,
+                      expectation_type="trials_tapers"):
+    """Imaginary part of sum_{f1<f2} conj(c[f1]) c[f2] over the (band-passed, subsampled) non-negative
+    frequencies of the coherency (connectivity.py:1587-1650; _bandpass :2040-2073 keeps lo < f < hi,
+    _get_independent_frequency_step :2076-2100, _inner_combination :1652-1676)."""
+    c = coherency(coef, expectation_type)
+    f = non_negative_frequencies(np.asarray(freqs))
+    if frequencies_of_interest is not None:
+        keep = (frequencies_of_interest[0] < f) & (f < frequencies_of_interest[1])
+        c = c[..., keep, :, :]
+    step = 1 if frequency_resolution is None else int(np.ceil(frequency_resolution / (freqs[1] - freqs[0])))
+    c = c[..., np.arange(0, c.shape[-3], step), :, :]
+    i1, i2 = np.array(list(combinations(range(c.shape[-3]), 2))).T
+    return (np.conj(c[..., i1, :, :]) * c[..., i2, :, :]).sum(axis=-3).imag
+
+
 # --------------------------------------------------------------------------- #
 def _herm(a):
     return np.conj(np.swapaxes(a, -1, -2))

@@ -27,6 +27,7 @@ SIGNATURES = {
     "sc_csm": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_float, c_int, _P, _P]),
     "sc_csm_simt": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_float, c_int, _P, _P]),
     "sc_pairwise_epilogue": (c_int, [c_int, _P, _P, c_int64, c_int64, c_int64, c_double, _P, _P]),
+    "sc_phase_slope_index": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, _P, _P]),
     "sc_wilson2": (c_int, [_P, c_int64, c_int, c_double, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
     "sc_granger_pairwise": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int64, _P, c_int64, c_double, c_int,
                                     c_int, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P]),

@@ -815,8 +815,44 @@ class Connectivity:
     def delay(self, *args, **kwargs):
         self._next_round("delay")
 
-    def phase_slope_index(self, *args, **kwargs):
-        self._next_round("phase_slope_index")
+    def phase_slope_index(self, frequencies_of_interest=None, frequency_resolution=None):
+        """Weighted average of the coherency phase slope projected on the imaginary axis, shape
+        (..., n_signals, n_signals) (connectivity.py:1587-1650).  The coherency of each window chunk stays on
+        the device; the band-pass (lo < f < hi) and the independent-frequency subsampling are index work done
+        on the host with the reference's formulas."""
+        lib = _lib.load()
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        fnn = nfft // 2 + 1
+        freqs = np.asarray(self.frequencies)
+        keep = np.arange(fnn)
+        if frequencies_of_interest is not None:
+            keep = np.flatnonzero((frequencies_of_interest[0] < freqs) & (freqs < frequencies_of_interest[1]))
+        step = 1
+        if frequency_resolution is not None:  # connectivity.py:2076-2100
+            step = int(np.ceil(frequency_resolution / (freqs[1] - freqs[0])))
+        keep = keep[np.arange(0, keep.size, step)]
+        if keep.size < 2:
+            raise IndexError("phase_slope_index needs at least two frequencies in the band of interest")
+        fidx = torch.from_numpy(keep.astype(np.int32)).to(self._device)
+        kept = self._kept_dims()
+        n_batch = int(np.prod(kept)) if kept else 1
+        scale = 1.0 / self.n_observations
+        out = torch.empty((n_batch, n_sig, n_sig), dtype=torch.float32, device=self._device)
+        st = _lib.stream_ptr()
+        for b0, b1, xp, nr in self._chunks(fnn):
+            nb = b1 - b0
+            power = torch.empty((nb, fnn, n_sig), dtype=torch.float32, device=self._device)
+            csm = torch.empty((nb, fnn, n_sig, n_sig), dtype=torch.complex64, device=self._device)
+            _lib.check(lib.sc_power(_lib.ptr(xp), nb, fnn, nr, n_sig, scale, _lib.ptr(power), st), "sc_power")
+            _lib.check(lib.sc_csm(_lib.ptr(xp), nb, fnn, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(csm), st), "sc_csm")
+            self._allreduce(power)
+            self._allreduce(csm)
+            del xp
+            _lib.check(lib.sc_pairwise_epilogue(_lib.M_COHERENCY, _lib.ptr(csm), _lib.ptr(power), nb, fnn, n_sig,
+                                                float(self.n_observations), _lib.ptr(csm), st), "sc_pairwise_epilogue")
+            _lib.check(lib.sc_phase_slope_index(_lib.ptr(csm), nb, fnn, n_sig, _lib.ptr(fidx), int(keep.size),
+                                                _lib.ptr(out[b0:b1]), st), "sc_phase_slope_index")
+        return self._finish(out.reshape(kept + (n_sig, n_sig)))
 
 
 def all_pairs(n_signals):

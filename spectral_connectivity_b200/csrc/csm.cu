@@ -303,6 +303,25 @@ __global__ void __launch_bounds__(256) coherence_epilogue_vec_kernel(int measure
     }
 }
 
+// phase_slope_index (connectivity.py:1587-1650): Im sum_{f1 < f2} conj(c[f1]) c[f2] over the selected bins =
+// sum_{f2} Im(conj(prefix(f2)) c[f2]) -- one pass with a running prefix instead of the reference's n(n-1)/2
+// products.  One thread per (b, i, j), coalesced along j; fp64 accumulators.
+__global__ void psi_kernel(const float2* __restrict__ coh, long long B, long long F, long long SS,
+                           const int* __restrict__ fidx, int nsel, float* __restrict__ out) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < B * SS;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long b = e / SS, ij = e - b * SS;
+        double px = 0.0, py = 0.0, acc = 0.0;
+        for (int q = 0; q < nsel; ++q) {
+            const float2 c = coh[(b * F + fidx[q]) * SS + ij];
+            acc += px * c.y - py * c.x;
+            px += c.x;
+            py += c.y;
+        }
+        out[e] = (float)acc;
+    }
+}
+
 unsigned grid_for(long long total, int threads) {
     long long blocks = (total + threads - 1) / threads;
     const long long cap = (long long)sc_num_sms() * 32;
@@ -374,6 +393,16 @@ extern "C" int sc_pairwise_epilogue(int measure, const void* in0, const float* i
     const long long cap = (long long)sc_num_sms() * 64;
     epilogue_kernel<<<(unsigned)(rows < cap ? rows : cap), threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         measure, reinterpret_cast<const float*>(in0), in1, B * F, S, n_observations, reinterpret_cast<float*>(out));
+    SC_LAUNCH_OK();
+    return SC_OK;
+}
+
+extern "C" int sc_phase_slope_index(const void* coherency_c64, int64_t B, int64_t F, int64_t S, const int* freq_index,
+                                    int n_selected, float* out, void* stream) {
+    SC_CHECK_ARG(coherency_c64 && freq_index && out, "sc_phase_slope_index: null pointer");
+    SC_CHECK_ARG(B > 0 && F > 0 && S > 0 && n_selected >= 0, "sc_phase_slope_index: bad size");
+    psi_kernel<<<grid_for(B * S * S, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(coherency_c64), B, F, S * S, freq_index, n_selected, out);
     SC_LAUNCH_OK();
     return SC_OK;
 }

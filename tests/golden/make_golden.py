@@ -36,8 +36,26 @@ def series(seed, n, t, s, fs):
     return synthetic_series(n, t, s, fs, seed)
 
 
+def psi_section(T, C):
+    """phase_slope_index (connectivity.py:1587-1650) on the section-4 input: whole band, a band of
+    interest, and a band with a frequency resolution (independent-frequency subsampling)."""
+    psi = {}
+    x = series(7, 300, 4, 4, 100.0)
+    m = T.Multitaper(x, sampling_frequency=100.0, time_halfbandwidth_product=3, time_window_duration=1.0)
+    c = C.Connectivity.from_multitaper(m)
+    psi["x"] = x
+    psi["meta"] = np.array([100.0, 3.0, 1.0])
+    psi["all"] = np.asarray(c.phase_slope_index())
+    psi["band"] = np.asarray(c.phase_slope_index(frequencies_of_interest=[5.0, 30.0]))
+    psi["band_res"] = np.asarray(c.phase_slope_index(frequencies_of_interest=[2.0, 45.0], frequency_resolution=3.5))
+    np.savez_compressed(os.path.join(HERE, "psi.npz"), **psi)
+
+
 def main():
     T, C, M = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "psi":
+        psi_section(T, C)
+        return
     np.random.seed(42)
 
     # ---- 1. index arithmetic (bit exact) ---------------------------------
@@ -169,6 +187,7 @@ def main():
     sv["global_coherence"] = np.asarray(gc_)[..., :1]
     sv["global_vectors"] = np.asarray(gv_)[..., :1]
     np.savez_compressed(os.path.join(HERE, "svd_measures.npz"), **sv)
+    psi_section(T, C)
     print("golden fixtures written to", HERE)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

@@ -609,3 +609,30 @@ def test_granger_and_mvar_general_two_sided_coefficients(sc):
     assert_parity(got, ref, 2e-5, "granger, general two-sided")
     h, sigma = O.mvar_transfer_function(csm)
     assert_parity(c.directed_transfer_function(), O.directed_transfer_function(h), 2e-5, "DTF, general two-sided")
+
+
+# --------------------------------------------------------------------------- #
+# phase slope index
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("kw", [{}, dict(frequencies_of_interest=[5.0, 30.0]),
+                                dict(frequencies_of_interest=[2.0, 45.0], frequency_resolution=3.5)])
+def test_phase_slope_index_golden(sc, kw):
+    g = golden("psi.npz")
+    fs, nw, dur = g["meta"]
+    m = sc.Multitaper(g["x"], sampling_frequency=fs, time_halfbandwidth_product=nw, time_window_duration=dur)
+    c = sc.Connectivity.from_multitaper(m)
+    key = "all" if not kw else ("band_res" if "frequency_resolution" in kw else "band")
+    assert_parity(c.phase_slope_index(**kw), g[key], TOL, f"PSI {key}")
+    with pytest.raises(IndexError):
+        c.phase_slope_index(frequencies_of_interest=[10.0, 10.5])
+
+
+def test_phase_slope_index_vs_oracle_larger(sc):
+    fs = 500.0
+    x = O.synthetic_series(1500, 5, 64, fs, seed=31).astype(np.float32)
+    m = sc.Multitaper(x, sampling_frequency=fs, time_halfbandwidth_product=3, time_window_duration=0.5)
+    c = sc.Connectivity.from_multitaper(m, max_chunk_bytes=1 << 20)   # several window chunks
+    got = c.phase_slope_index(frequencies_of_interest=[8.0, 120.0], frequency_resolution=5.0)
+    coef = O.multitaper_fft(x.astype(np.float64), fs, O.dpss_tapers(250, 3, 5, fs), 250, 250, 250)
+    ref = O.phase_slope_index(coef, O.frequencies(250, fs), [8.0, 120.0], 5.0)
+    assert_parity(got, ref, TOL, "PSI S=64")

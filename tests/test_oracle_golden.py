@@ -146,3 +146,18 @@ def test_svd_measures():
     # eigenvectors agree up to a unit-modulus factor
     overlap = np.abs(np.sum(np.conj(gv) * g["global_vectors"], axis=-2))
     assert np.allclose(overlap, 1.0, atol=1e-6)
+
+
+PSI_CASES = {"all": {}, "band": dict(frequencies_of_interest=[5.0, 30.0]),
+             "band_res": dict(frequencies_of_interest=[2.0, 45.0], frequency_resolution=3.5)}
+
+
+@pytest.mark.parametrize("case", list(PSI_CASES))
+def test_phase_slope_index(case):
+    g = golden("psi.npz")
+    fs, nw, dur = g["meta"]
+    n, step, nfft = O.window_geometry(g["x"].shape[0], fs, dur)
+    taps = O.dpss_tapers(n, nw, O.default_n_tapers(nw), fs)
+    coef = O.multitaper_fft(g["x"], fs, taps, n, step, nfft)
+    got = O.phase_slope_index(coef, O.frequencies(nfft, fs), **PSI_CASES[case])
+    assert_parity(got, g[case], 1e-9, f"PSI {case}")
