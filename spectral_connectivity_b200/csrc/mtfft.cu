@@ -40,6 +40,18 @@ struct CtaSync {
 };
 struct DynPlan {};  // runtime plan (any nfft)
 
+// Shared-memory slab tile[j][TS] (one row of TS floats per sample): the taper product reads one float2 (two
+// series) per thread with the SAMPLE index along the lanes, i.e. at a stride of one row -- 8 lanes per bank
+// pair for TS = 8.  XOR-swizzling the float2 slot of a row with the sample bits just above the bank period makes
+// those reads conflict-free while the row-wise loads/stores stay a permutation within each row.
+template <int TS>
+__device__ __forceinline__ int tile_ix(int j, int s) {
+    constexpr int NP = TS / 2;
+    if (NP <= 1) return j * TS + s;
+    constexpr int SH = NP == 2 ? 3 : (NP == 4 ? 2 : (NP == 8 ? 1 : 0));  // row stride = NP bank pairs of 16
+    return j * TS + ((((s >> 1) ^ ((j >> SH) & (NP - 1))) << 1) | (s & 1));
+}
+
 template <int TS, bool WS, typename PLAN>
 __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtParams p) {
     constexpr bool STATIC = !std::is_same<PLAN, DynPlan>::value;
@@ -101,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
             for (int u = 0; u < LD; ++u) {
                 const int j = j0 + u * JSTEP;
                 if (j < n) {
-                    if (!WS) tile[j * TS + sl] = v[u];
+                    if (!WS) tile[tile_ix<TS>(j, sl)] = v[u];
                     bad |= !isfinite(v[u]);
                     sum += v[u];
                     if (p.detrend == SC_DETREND_LINEAR) sumu += ((j + 1.0) / n - ubar) * v[u];
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
         if (!WS && p.detrend != SC_DETREND_NONE) {
             const float ta = trend_a[sl], tb = trend_b[sl];
             const float invn = 1.0f / n;
-            for (int j = jr; j < ncopy; j += JSTEP) tile[j * TS + sl] -= ta * ((j + 1) * invn) + tb;
+            for (int j = jr; j < ncopy; j += JSTEP) tile[tile_ix<TS>(j, sl)] -= ta * ((j + 1) * invn) + tb;
             __syncthreads();
         }
 
@@ -163,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
                                 v1 -= trend_a[sa + 1] * u + trend_b[sa + 1];
                             }
                         } else {
-                            v0 = tile[j * TS + sa];
+                            v0 = tile[tile_ix<TS>(j, sa)];
                         }
                         z = cmake<float>(v0 * hv, v1 * hv);
                     }
@@ -174,10 +186,10 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
 #pragma unroll 2
                 for (int j = threadIdx.x; j < nfft; j += kThreads) {
                     const float hv = j < ncopy ? __ldg(h + j) : 0.f;
-                    const float* trow = tile + (size_t)(j < ncopy ? j : 0) * TS;
+                    const int jt = j < ncopy ? j : 0;
 #pragma unroll
                     for (int pp = 0; pp < NP; ++pp) {
-                        const float2 v = *reinterpret_cast<const float2*>(trow + 2 * pp);
+                        const float2 v = *reinterpret_cast<const float2*>(tile + tile_ix<TS>(jt, 2 * pp));
                         bufA[(size_t)pp * nfft + j] = cmake<float>(v.x * hv, v.y * hv);
                     }
                 }

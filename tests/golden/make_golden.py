@@ -51,10 +51,36 @@ def psi_section(T, C):
     np.savez_compressed(os.path.join(HERE, "psi.npz"), **psi)
 
 
+def series_512(n=120, n_trials=128, s=512, seed=55):
+    """White noise + lag-1 even->odd coupling (no common sinusoid: with 1152 observations for 512 channels the
+    reference's Wilson iteration diverges on the SURVEY.md 8(d) recipe, whose 40 Hz line makes the CSM
+    ill-conditioned).  float32-representable so that the device sees the same samples."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, n_trials, s)).astype(np.float32)
+    x[1:, :, 1::2] += 0.5 * x[:-1, :, 0::2]
+    return x
+
+
+def dtf512_section(T, C):
+    """BASELINE config-5 geometry on ONE window: 512 channels x 128 trials, 120 samples @ 2 kHz, NW = 5 (9 tapers);
+    directed_transfer_function through the live reference (blocks=32 keeps the un-averaged CSM at 0.6 GB per
+    block; two full-matrix Wilson factorisations of 120 x 512 x 512).  Takes ~15 minutes; only a slice is kept."""
+    x = series_512().astype(np.float64)
+    m = T.Multitaper(x, sampling_frequency=2000.0, time_halfbandwidth_product=5, time_window_duration=0.060)
+    c = C.Connectivity.from_multitaper(m, blocks=32)
+    dtf = np.asarray(c.directed_transfer_function())
+    assert dtf.shape == (1, 61, 512, 512), dtf.shape
+    np.savez_compressed(os.path.join(HERE, "dtf512.npz"), rows=dtf[0, ::6, :32, :],
+                        row_sums=dtf.sum(axis=-1)[0], col_mean=dtf.mean(axis=-2)[0, ::6])
+
+
 def main():
     T, C, M = load_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "psi":
         psi_section(T, C)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "dtf512":
+        dtf512_section(T, C)
         return
     np.random.seed(42)
 
