@@ -7,8 +7,8 @@
 // Matrices are row-major c128, batch-contiguous [count][S][S].  A "window state" array (0 = active) lets
 // the Wilson loop skip converged / failed windows: matrix b belongs to window b / n_inner.
 //
-// Inversion.  In-place blocked Gauss-Jordan (panel width nb = 32 for S <= 256, 16 above, so that the S x nb
-// panel fits in shared memory): for each column panel J
+// Inversion.  In-place blocked Gauss-Jordan (panel width nb = 32 up to S = 420, 24 at S = 512, ... so that the
+// S x nb panel fits in shared memory): for each column panel J
 //   zb_panel_kernel   one CTA per matrix: unblocked in-place GJ with partial pivoting (rows >= current column)
 //                     on the panel in shared memory -> T_J (S x nb: rows J hold A_JJ^-1, the others
 //                     -A_iJ A_JJ^-1) and the pivot rows; then the same CTA gathers the row block
@@ -309,8 +309,8 @@ __global__ void __launch_bounds__(256) zb_panel_kernel(const ZInvParams p) {
 
 // M[i, c] <- (i in J ? 0 : M[i, c]) + sum_k T_J[i, k] RB[k, c]  (c outside J);  M[:, J] <- T_J
 __global__ void __launch_bounds__(256) zb_update_kernel(const ZInvParams p) {
-    __shared__ cd Ts[16][kZP];
-    __shared__ cd Rs[16][kZP];
+    __shared__ cd Ts[8][kZP];
+    __shared__ cd Rs[8][kZP];
     const int S = p.S, w = p.w, j0 = p.j0;
     const int tiles = (S + kZT - 1) / kZT;
     const long long b = blockIdx.x / (tiles * tiles);
@@ -331,11 +331,11 @@ __global__ void __launch_bounds__(256) zb_update_kernel(const ZInvParams p) {
             const bool in_j = m >= j0 && m < j0 + w;
             acc[i][j] = (m < S && n < S && !in_j) ? M[(size_t)m * S + n] : zero;
         }
-    for (int k0 = 0; k0 < w; k0 += 16) {
+    for (int k0 = 0; k0 < w; k0 += 8) {  // panel widths are multiples of 8 (the last panel is zero-filled)
         __syncthreads();
-        for (int e = tid; e < 16 * kZT; e += 256) {
+        for (int e = tid; e < 8 * kZT; e += 256) {
             {
-                const int m = e / 16, k = e % 16;
+                const int m = e / 8, k = e % 8;
                 Ts[k][m] = (m0 + m < S && k0 + k < w) ? TJ[(size_t)(m0 + m) * p.nb + k0 + k] : zero;
             }
             {
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) zb_update_kernel(const ZInvParams p) {
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < 8; ++k) {
             cd a[4], bb[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i] = Ts[k][ty + 16 * i];
@@ -399,7 +399,13 @@ __global__ void zb_shift_copy_kernel(const cd* src, const double* src_real, doub
     }
 }
 
-inline int zb_panel_width(int S) { return S <= 256 ? 32 : 16; }
+// widest panel (multiple of 8, at most 32) whose S x (nb + 1) c128 image fits in shared memory:
+// 32 up to S = 420, 24 at S = 512, 8 at S = 1024
+inline int zb_panel_width(int S) {
+    int nb = (int)(((size_t)sc_max_smem_optin() - 4096) / ((size_t)S * sizeof(cd))) - 1;
+    nb &= ~7;
+    return nb > 32 ? 32 : (nb < 8 ? 8 : nb);
+}
 
 inline size_t zb_panel_smem(int S, int nb) {
     return (size_t)S * (nb + 1) * sizeof(cd) + (size_t)nb * sizeof(cd) + 8 * sizeof(double) + 8 * sizeof(int) +
@@ -408,7 +414,7 @@ inline size_t zb_panel_smem(int S, int nb) {
 
 // bytes of the TJ / RB / pivot scratch of a batched inversion
 inline int64_t zb_inverse_scratch_bytes(int64_t count, int S) {
-    const int nb = zb_panel_width(S);
+    const int nb = 32;  // upper bound of zb_panel_width: the query must not depend on the device
     return count * ((int64_t)2 * S * nb * (int64_t)sizeof(cd) + (int64_t)S * 8 + 16) + 256;
 }
 
@@ -574,5 +580,89 @@ __global__ void zb_mvar_measure_kernel(int measure, const cd* h, const cd* a, co
             default: v = sqrt(h2 / inflow_all[w * S + i]) * sqrt(a2 / cs[wf * S + j]); break;
         }
         out[e] = (float)v;
+    }
+}
+
+// Causal projection (plus operator, mpd.py:96-142) for large matrices: one CTA owns a 4 x 4 tile of matrix
+// entries, so that every (frequency, tile row) access is a 64-byte segment instead of wg_plus_kernel's single
+// 16-byte elements at a stride of S*S*16 bytes.  The 16 lag sequences are transformed as one batch (sequence
+// stride N + 1: conflict-free when the lanes run over the entries).  For real time series (herm) only tiles on or
+// above the diagonal are launched; the tile's entries i <= j also produce their mirror images (j, i).
+constexpr int kPT = 4;
+constexpr int kPE = kPT * kPT;
+
+inline size_t zb_plus_smem(int nfft) { return ((size_t)2 * kPE * (nfft + 1) + nfft) * sizeof(cd); }
+
+__global__ void __launch_bounds__(kThreads) wg_plus_tile_kernel(const WgParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = p.nfft, S = p.S, NS = N + 1;
+    const size_t SS = (size_t)S * S;
+    cd* ZA = reinterpret_cast<cd*>(smem_raw);
+    cd* ZB = ZA + (size_t)kPE * NS;
+    cd* tws = ZB + (size_t)kPE * NS;
+    const long long w = blockIdx.y;
+    if (p.state[w] != 0) return;
+    const int T = (S + kPT - 1) / kPT;
+    int ti, tj;
+    if (p.herm) {  // blockIdx.x enumerates ti <= tj
+        int k = blockIdx.x;
+        ti = 0;
+        while (k >= T - ti) {
+            k -= T - ti;
+            ++ti;
+        }
+        tj = ti + k;
+    } else {
+        ti = blockIdx.x / T;
+        tj = blockIdx.x % T;
+    }
+    const int i0 = ti * kPT, j0 = tj * kPT;
+    for (int q = threadIdx.x; q < N; q += kThreads) tws[q] = p.tw[q];
+    cd* base = p.bp + (size_t)w * p.F * SS;
+    const cd zero = cmake<double>(0.0, 0.0);
+    for (int idx = threadIdx.x; idx < p.F * kPE; idx += kThreads) {
+        const int f = idx / kPE, e = idx % kPE;
+        const int i = i0 + e / kPT, j = j0 + e % kPT;
+        const bool valid = i < S && j < S && (!p.herm || i <= j);
+        const cd v = valid ? base[(size_t)f * SS + (size_t)i * S + j] : zero;
+        ZA[e * NS + f] = v;
+        if (p.herm && f != 0 && 2 * f != N) ZA[e * NS + N - f] = cconj(v);
+    }
+    __syncthreads();
+    cd* c = sc_cta_fft<double, true>(ZA, ZB, kPE, NS, p.plan, tws, true);
+    cd* o = (c == ZA) ? ZB : ZA;
+    const double inv_n = 1.0 / N;
+    const int kcut = (N + 1) / 2;
+    for (int idx = threadIdx.x; idx < N * kPE; idx += kThreads) {
+        const int k = idx / kPE, e = idx % kPE;
+        const int i = i0 + e / kPT, j = j0 + e % kPT;
+        cd y = zero;
+        if (k < kcut) {
+            const double wgt = k == 0 ? 0.5 * inv_n : inv_n;
+            if (p.herm) {
+                const double cij = c[e * NS + k].x;
+                const double cji = (i == j) ? 0.0 : (k == 0 ? 0.0 : c[e * NS + N - k].x);
+                y = cmake<double>(cij * wgt, cji * wgt);
+            } else {
+                y = (k == 0 && i > j) ? zero : cscale(c[e * NS + k], wgt);
+            }
+        }
+        o[e * NS + k] = y;
+    }
+    __syncthreads();
+    const cd* Q = sc_cta_fft<double, true>(o, c, kPE, NS, p.plan, tws, false);
+    for (int idx = threadIdx.x; idx < p.F * kPE; idx += kThreads) {
+        const int f = idx / kPE, e = idx % kPE;
+        const int i = i0 + e / kPT, j = j0 + e % kPT;
+        if (i >= S || j >= S) continue;
+        if (p.herm) {
+            if (i > j) continue;
+            const cd a = Q[e * NS + f], m = Q[e * NS + (f == 0 ? 0 : N - f)];
+            base[(size_t)f * SS + (size_t)i * S + j] = cmake<double>(0.5 * (a.x + m.x), 0.5 * (a.y - m.y));
+            if (i != j)
+                base[(size_t)f * SS + (size_t)j * S + i] = cmake<double>(0.5 * (a.y + m.y), 0.5 * (m.x - a.x));
+        } else {
+            base[(size_t)f * SS + (size_t)i * S + j] = Q[e * NS + f];
+        }
     }
 }

@@ -301,12 +301,12 @@ __global__ void wg_finish_kernel(const int* state, int* flags, long long B) {
 }
 
 // ---- MVAR quantities ------------------------------------------------------------------------------
-// H0 = Re ifft(G)[lag 0] per window (connectivity.py:1705, 1739-1740)
+// H0 = Re ifft(G)[lag 0] per window (connectivity.py:1705, 1739-1740); grid (entry chunks, windows)
 __global__ void mvar_lag0_kernel(const cd* g, long long B, int F, int nfft, int herm, int S, double* h0) {
-    const long long w = blockIdx.x;
+    const long long w = blockIdx.y;
     const int SS = S * S;
     const cd* src = g + (size_t)w * F * SS;
-    for (int e = threadIdx.x; e < SS; e += blockDim.x) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < SS; e += gridDim.x * blockDim.x) {
         double acc = 0.0;
         for (int f = 0; f < F; ++f) acc += bin_weight(f, nfft, herm) * src[(size_t)f * SS + e].x;
         h0[(size_t)w * SS + e] = acc / nfft;
@@ -465,11 +465,19 @@ int wilson_blocked(WgParams p, int max_iterations, cd* out_g, int* out_iters, in
     p.iters = reinterpret_cast<int*>(tail + (size_t)B * 16);
     double* lag0 = reinterpret_cast<double*>(tail + (((size_t)B * 32 + 255) / 256) * 256);
     unsigned char* scratch = reinterpret_cast<unsigned char*>(lag0) + (((size_t)B * S * S * 8 + 255) / 256) * 256;
-    const size_t plus_smem = (size_t)3 * p.nfft * sizeof(cd);
-    if (plus_smem > 48 * 1024)
+    size_t plus_smem = (size_t)3 * p.nfft * sizeof(cd);
+    const bool tile_plus = zb_plus_smem(p.nfft) <= (size_t)sc_max_smem_optin() - 2048;  // 16 sequences fit
+    if (tile_plus) {
+        plus_smem = zb_plus_smem(p.nfft);
+        if (plus_smem > 48 * 1024)
+            SC_CUDA_OK(cudaFuncSetAttribute(wg_plus_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plus_smem));
+    } else if (plus_smem > 48 * 1024) {
         SC_CUDA_OK(cudaFuncSetAttribute(wg_plus_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plus_smem));
+    }
+    const int n_t = (S + kPT - 1) / kPT;
+    const int n_tiles = p.herm ? n_t * (n_t + 1) / 2 : n_t * n_t;
     // lag-0 covariance -> Cholesky -> G0 = L^T for every frequency
-    mvar_lag0_kernel<<<(unsigned)B, 256, 0, st>>>(p.csm, B, F, p.nfft, p.herm, S, lag0);
+    mvar_lag0_kernel<<<dim3((unsigned)((S * S + 255) / 256), (unsigned)B), 256, 0, st>>>(p.csm, B, F, p.nfft, p.herm, S, lag0);
     zb_cholesky_kernel<<<(unsigned)B, 1024, (size_t)S * sizeof(double), st>>>(lag0, S, p.state, p.iters, p.err);
     cd* gcur = out_g;
     cd* free_a = w0;
@@ -494,7 +502,8 @@ int wilson_blocked(WgParams p, int max_iterations, cd* out_g, int* out_iters, in
         g.A = free_a; g.Bm = free_b; g.C = bp; g.conj_b = 1; g.add_identity = 1;
         zb_gemm(g, count, st);
         p.bp = bp;
-        wg_plus_kernel<<<dim3(n_entries, (unsigned)B), kThreads, plus_smem, st>>>(p);
+        if (tile_plus) wg_plus_tile_kernel<<<dim3(n_tiles, (unsigned)B), kThreads, plus_smem, st>>>(p);
+        else wg_plus_kernel<<<dim3(n_entries, (unsigned)B), kThreads, plus_smem, st>>>(p);
         // G <- G P -> free_a, max |dG| per window; converged windows are copied through
         g.A = gcur; g.Bm = bp; g.C = free_a; g.conj_b = 0; g.add_identity = 0; g.passthrough = 1; g.err = p.err;
         zb_gemm(g, count, st);
@@ -599,7 +608,8 @@ extern "C" int sc_mvar_lag0(const void* g_c128, int64_t B, int F, int nfft, int 
                             void* stream) {
     SC_CHECK_ARG(g_c128 && out_h0 && B > 0 && F > 0, "sc_mvar_lag0: bad argument");
     if (int rc = check_s(S, "sc_mvar_lag0")) return rc;
-    mvar_lag0_kernel<<<(unsigned)B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    SC_CHECK_ARG(B <= 65535, "sc_mvar_lag0: at most 65535 windows per call");
+    mvar_lag0_kernel<<<dim3((unsigned)((S * S + 255) / 256), (unsigned)B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const cd*>(g_c128), B, F, nfft, hermitian_half ? 1 : 0, S, out_h0);
     SC_LAUNCH_OK();
     return SC_OK;
