@@ -111,6 +111,11 @@ int sc_csm(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, float sc
 int sc_csm_simt(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, float scale, int mode, void* out,
                 void* stream);
 
+/* power as the real diagonal of an expected cross-spectral matrix that has been computed anyway
+ * (connectivity.py:441-445: E[|X_i|^2] = E[X_i conj X_i]): csm c64 [BF][S][S] -> f32 [BF][S].  Saves the
+ * second pass over the coefficients that sc_power needs. */
+int sc_power_from_csm(const void* csm_c64, int64_t BF, int64_t S, float* out, void* stream);
+
 /* coherency / coherence_magnitude / coherence_phase / imaginary_coherence (connectivity.py:632-743),
  * phase_locking_value / pairwise_phase_consistency (:905-931, :1129-1159), phase_lag_index,
  * weighted / debiased variants (:933-1127): element-wise epilogues on [B][F][S][S]. */

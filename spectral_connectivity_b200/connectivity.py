@@ -335,14 +335,6 @@ class Connectivity:
         for b0, b1, xp, nr in self._chunks(n_freq):
             nb = b1 - b0
             power = csm = None
-            if need_power:
-                power = torch.empty((nb, n_freq, n_sig), dtype=torch.float32, device=dev)
-                with _lib.timed("power"):
-                    _lib.check(lib.sc_power(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.ptr(power), st), "sc_power")
-                self._allreduce(power)
-                if "power" in out:
-                    out["power"][b0:b1] = power
-                    offload("power", b0, b1)
             if "csm" in needs:
                 csm = torch.empty((nb, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
                 with _lib.timed("csm"):
@@ -352,6 +344,19 @@ class Connectivity:
                 if "expectation_cross_spectral_matrix" in out:
                     out["expectation_cross_spectral_matrix"][b0:b1] = csm
                     offload("expectation_cross_spectral_matrix", b0, b1)
+            if need_power:
+                power = torch.empty((nb, n_freq, n_sig), dtype=torch.float32, device=dev)
+                with _lib.timed("power"):
+                    if csm is not None:  # the diagonal of the CSM: no second pass over the coefficients
+                        _lib.check(lib.sc_power_from_csm(_lib.ptr(csm), nb * n_freq, n_sig, _lib.ptr(power), st),
+                                   "sc_power_from_csm")
+                    else:
+                        _lib.check(lib.sc_power(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.ptr(power), st),
+                                   "sc_power")
+                        self._allreduce(power)
+                if "power" in out:
+                    out["power"][b0:b1] = power
+                    offload("power", b0, b1)
             plv = pli = None
             if "plv" in needs:
                 plv = torch.empty((nb, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
@@ -843,11 +848,10 @@ class Connectivity:
             nb = b1 - b0
             power = torch.empty((nb, fnn, n_sig), dtype=torch.float32, device=self._device)
             csm = torch.empty((nb, fnn, n_sig, n_sig), dtype=torch.complex64, device=self._device)
-            _lib.check(lib.sc_power(_lib.ptr(xp), nb, fnn, nr, n_sig, scale, _lib.ptr(power), st), "sc_power")
             _lib.check(lib.sc_csm(_lib.ptr(xp), nb, fnn, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(csm), st), "sc_csm")
-            self._allreduce(power)
             self._allreduce(csm)
             del xp
+            _lib.check(lib.sc_power_from_csm(_lib.ptr(csm), nb * fnn, n_sig, _lib.ptr(power), st), "sc_power_from_csm")
             _lib.check(lib.sc_pairwise_epilogue(_lib.M_COHERENCY, _lib.ptr(csm), _lib.ptr(power), nb, fnn, n_sig,
                                                 float(self.n_observations), _lib.ptr(csm), st), "sc_pairwise_epilogue")
             _lib.check(lib.sc_phase_slope_index(_lib.ptr(csm), nb, fnn, n_sig, _lib.ptr(fidx), int(keep.size),

@@ -406,3 +406,20 @@ extern "C" int sc_phase_slope_index(const void* coherency_c64, int64_t B, int64_
     SC_LAUNCH_OK();
     return SC_OK;
 }
+
+// power = real diagonal of the expected cross-spectral matrix (connectivity.py:441-445: E[|X_i|^2] = E[X_i conj X_i])
+__global__ void power_from_csm_kernel(const float2* __restrict__ csm, long long BF, long long S, float* __restrict__ out) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < BF * S;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long bf = e / S, i = e - bf * S;
+        out[e] = csm[(bf * S + i) * S + i].x;
+    }
+}
+
+extern "C" int sc_power_from_csm(const void* csm_c64, int64_t BF, int64_t S, float* out, void* stream) {
+    SC_CHECK_ARG(csm_c64 && out && BF > 0 && S > 0, "sc_power_from_csm: bad argument");
+    power_from_csm_kernel<<<grid_for(BF * S, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(csm_c64), BF, S, out);
+    SC_LAUNCH_OK();
+    return SC_OK;
+}
