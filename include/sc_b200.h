@@ -211,9 +211,13 @@ int sc_canonical_coherence(const void* csm_c64, int64_t B, int F, int S, const i
                            void* stream);
 
 /* global_coherence(max_rank=1) -- connectivity.py:822-895, 2245-2279: largest eigenvalue of each CSM
- * (c64 [BF][S][S], S <= 64) = top singular value^2 / n_observations, and its unit eigenvector (c64 [BF][S],
- * defined up to a phase like the reference's SVD output). */
-int sc_global_coherence(const void* csm_c64, int64_t BF, int S, float* out_value, void* out_vector_c64, void* stream);
+ * (c64 [BF][S][S]) = top singular value^2 / n_observations, and its unit eigenvector (c64 [BF][S], defined up
+ * to a phase like the reference's SVD output).  S <= 64: one CTA per matrix in shared memory, workspace NULL/0.
+ * S > 64 (up to 1024): repeated squaring with the tiled c128 GEMM, workspace
+ * sc_global_coherence_workspace_bytes(BF, S) -- callers chunk BF to bound it. */
+int sc_global_coherence(const void* csm_c64, int64_t BF, int S, float* out_value, void* out_vector_c64,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+int64_t sc_global_coherence_workspace_bytes(int64_t BF, int S);
 
 #ifdef __cplusplus
 }

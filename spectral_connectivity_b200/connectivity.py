@@ -805,13 +805,22 @@ class Connectivity:
             raise NotImplementedError("global_coherence on the device returns the leading component only (max_rank=1)")
         lib = _lib.load()
         n_win, n_trials, n_tapers, nfft, n_sig = self._shape
-        if n_sig > 64:
-            raise NotImplementedError("global_coherence on the device handles up to 64 signals")
+        if n_sig > 1024:
+            raise NotImplementedError("global_coherence on the device handles up to 1024 signals")
         csm = self._trials_tapers_csm(nfft)
         val = torch.empty((n_win, nfft, 1), dtype=torch.float32, device=self._device)
         vec = torch.empty((n_win, nfft, n_sig, 1), dtype=torch.complex64, device=self._device)
-        _lib.check(lib.sc_global_coherence(_lib.ptr(csm), n_win * nfft, n_sig, _lib.ptr(val), _lib.ptr(vec),
-                                           _lib.stream_ptr()), "sc_global_coherence")
+        n_mat = n_win * nfft
+        per = max(1, lib.sc_global_coherence_workspace_bytes(1, n_sig))
+        chunk = n_mat if n_sig <= 64 else max(1, min(n_mat, (8 << 30) // per))  # <= 8 GiB of squaring workspace
+        ws_bytes = lib.sc_global_coherence_workspace_bytes(chunk, n_sig)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=self._device)
+        csm_f, val_f, vec_f = csm.reshape(n_mat, n_sig, n_sig), val.reshape(n_mat), vec.reshape(n_mat, n_sig)
+        for m0 in range(0, n_mat, chunk):
+            m1 = min(n_mat, m0 + chunk)
+            _lib.check(lib.sc_global_coherence(_lib.ptr(csm_f[m0:m1]), m1 - m0, n_sig, _lib.ptr(val_f[m0:m1]),
+                                               _lib.ptr(vec_f[m0:m1]), _lib.ptr(ws) if ws_bytes else None, ws_bytes,
+                                               _lib.stream_ptr()), "sc_global_coherence")
         return self._finish(val), self._finish(vec)
 
     def group_delay(self, *args, **kwargs):

@@ -269,14 +269,25 @@ extern "C" int sc_canonical_coherence(const void* csm_c64, int64_t B, int F, int
     return SC_OK;
 }
 
+int64_t sc_global_coherence_blocked_workspace(int64_t BF, int S);
+int sc_global_coherence_blocked(const void* csm_c64, int64_t BF, int S, float* out_value, void* out_vector_c64,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+
+extern "C" int64_t sc_global_coherence_workspace_bytes(int64_t BF, int S) {
+    if (BF < 1 || S <= kMaxN) return 0;
+    return sc_global_coherence_blocked_workspace(BF, S);
+}
+
 extern "C" int sc_global_coherence(const void* csm_c64, int64_t BF, int S, float* out_value, void* out_vector_c64,
-                                   void* stream) {
+                                   void* workspace, int64_t workspace_bytes, void* stream) {
     SC_CHECK_ARG(csm_c64 && out_value && out_vector_c64 && BF > 0, "sc_global_coherence: bad argument");
-    if (S < 1 || S > kMaxN) {
-        sc_set_error("sc_global_coherence: S=%d outside [1, %d]", S, kMaxN);
+    SC_CHECK_ARG(BF < (1LL << 31), "sc_global_coherence: batch too large");
+    if (S < 1) {
+        sc_set_error("sc_global_coherence: S=%d", S);
         return SC_ERR_UNSUPPORTED;
     }
-    SC_CHECK_ARG(BF < (1LL << 31), "sc_global_coherence: batch too large");
+    if (S > kMaxN)  // tiled c128 GEMM squarings in global memory (wilson_general.cu)
+        return sc_global_coherence_blocked(csm_c64, BF, S, out_value, out_vector_c64, workspace, workspace_bytes, stream);
     const size_t smem = ((size_t)3 * S * S + S) * sizeof(cd);
     if (smem > 48 * 1024)
         SC_CUDA_OK(cudaFuncSetAttribute(global_coherence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

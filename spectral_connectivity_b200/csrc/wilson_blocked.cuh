@@ -31,6 +31,7 @@ struct ZGemmParams {
     const int* state;  // per outer index, may be null; != 0 -> skip (or copy A through, see passthrough)
     int passthrough;   // skipped batches copy A to C (keeps a ping-pong buffer pair consistent)
     double* err;       // per outer index, may be null: max |C - A| as an order-preserving bit pattern
+    int upper_only;    // skip tiles strictly below the diagonal (the consumer reads i <= j only)
 };
 
 constexpr int kZT = 64;   // C tile edge
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(256) zb_gemm_kernel(const ZGemmParams p) {
     const long long batch = blockIdx.x / (tiles * tiles);
     const int tile = (int)(blockIdx.x - batch * tiles * tiles);
     const int m0 = (tile / tiles) * kZT, n0 = (tile % tiles) * kZT;
+    if (p.upper_only && m0 > n0) return;
     const long long outer = batch / p.n_inner, inner = batch - outer * p.n_inner;
     const cd* A = p.A + outer * p.a_so + inner * p.a_si;
     const cd* Bm = p.Bm + outer * p.b_so + inner * p.b_si;

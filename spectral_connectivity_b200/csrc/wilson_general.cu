@@ -492,15 +492,17 @@ int wilson_blocked(WgParams p, int max_iterations, cd* out_g, int* out_iters, in
         SC_CUDA_OK(cudaMemcpyAsync(free_a, gcur, mat * sizeof(cd), cudaMemcpyDeviceToDevice, st));
         if (int rc = zb_inverse(free_a, free_b, count, S, p.state, F, nullptr, scratch, st)) return rc;
         ZGemmParams g;
-        g.n_inner = F; g.S = S; g.state = p.state; g.passthrough = 0; g.err = nullptr;
+        g.n_inner = F; g.S = S; g.state = p.state; g.passthrough = 0; g.err = nullptr; g.upper_only = 0;
         g.a_so = g.b_so = g.c_so = (long long)F * SS;
         g.a_si = g.b_si = g.c_si = SS;
         // T = Ginv S -> free_a
         g.A = free_b; g.Bm = p.csm; g.C = free_a; g.conj_b = 0; g.add_identity = 0;
         zb_gemm(g, count, st);
         // B = T Ginv^H + I -> bp
-        g.A = free_a; g.Bm = free_b; g.C = bp; g.conj_b = 1; g.add_identity = 1;
+        // (B is Hermitian; for real series the projection reads its upper triangle only)
+        g.A = free_a; g.Bm = free_b; g.C = bp; g.conj_b = 1; g.add_identity = 1; g.upper_only = p.herm;
         zb_gemm(g, count, st);
+        g.upper_only = 0;
         p.bp = bp;
         if (tile_plus) wg_plus_tile_kernel<<<dim3(n_tiles, (unsigned)B), kThreads, plus_smem, st>>>(p);
         else wg_plus_kernel<<<dim3(n_entries, (unsigned)B), kThreads, plus_smem, st>>>(p);
@@ -639,7 +641,7 @@ extern "C" int sc_mvar_transfer(const void* g_c128, const double* h0, double lam
         g.A = reinterpret_cast<const cd*>(g_c128); g.Bm = minv; g.C = reinterpret_cast<cd*>(out_h_c128);
         g.a_so = (long long)F * SS; g.a_si = SS; g.b_so = SS; g.b_si = 0; g.c_so = (long long)n_freq_out * SS; g.c_si = SS;
         g.n_inner = n_freq_out; g.S = S; g.conj_b = 0; g.add_identity = 0; g.state = nullptr; g.passthrough = 0;
-        g.err = nullptr;
+        g.err = nullptr; g.upper_only = 0;
         zb_gemm(g, B * n_freq_out, st);
         if (out_sigma) zb_sigma_kernel<<<grid_for(B * SS, 256), 256, 0, st>>>(h0, B, S, out_sigma);
         SC_LAUNCH_OK();
@@ -712,6 +714,151 @@ extern "C" int sc_mvar_measure(int measure, const void* h_c128, const void* a_c1
     const size_t smem = (size_t)(2 * S * S + 2 * S) * sizeof(double);
     mvar_measure_kernel<<<(unsigned)(B * F), 128, smem, st>>>(measure, reinterpret_cast<const cd*>(h_c128),
                                                                reinterpret_cast<const cd*>(a_c128), sigma, scratch, F, S, out);
+    SC_LAUNCH_OK();
+    return SC_OK;
+}
+
+// ---- global coherence for S > 64 (svd_measures.cu keeps S <= 64 in shared memory) --------------------------
+// Largest eigenvalue / eigenvector of each Hermitian PSD cross-spectral matrix by repeated squaring of the
+// trace-normalised matrix (same scheme as svd_measures.cu: tr(P^2) reaches 1 when P has rank one), with the
+// squarings done by the tiled c128 GEMM; a per-matrix state stops the work of converged matrices.
+namespace {
+
+constexpr int kGcSquarings = 32;
+
+__global__ void __launch_bounds__(256) gc_init_kernel(const float2* csm, int S, cd* P, int* state) {
+    __shared__ double red[8];
+    const long long b = blockIdx.x;
+    const size_t nn = (size_t)S * S;
+    const float2* m = csm + b * nn;
+    double t = 0.0;
+    for (int i = threadIdx.x; i < S; i += 256) t += m[(size_t)i * S + i].x;
+    double v[1] = {t};
+    block_sum<1>(v, red);
+    const double sc = v[0] > 0.0 ? 1.0 / v[0] : 0.0;
+    for (size_t e = threadIdx.x; e < nn; e += 256) {  // Hermitian part (real diagonal), trace 1
+        const int i = (int)(e / S), j = (int)(e % S);
+        const float2 a = m[e], t = m[(size_t)j * S + i];
+        P[b * nn + e] = cmake<double>(0.5 * ((double)a.x + t.x) * sc, 0.5 * ((double)a.y - t.y) * sc);
+    }
+    if (threadIdx.x == 0) state[b] = 0;
+}
+
+// Q <- Q / tr(Q); converged when 1 - Re tr(Q) < 1e-13 (tr(Q) = tr(P^2) with tr(P) = 1).  The division uses the
+// COMPLEX trace: the input diagonal carries imaginary rounding noise (~1e-10 relative from the fp32 CSM), i.e. a
+// component (1 + i b) * projector, and squaring doubles b every step while a real normalisation cannot remove
+// it (b^2 then exceeds the convergence threshold and the iteration runs away: measured before this fix).
+__global__ void __launch_bounds__(256) gc_norm_kernel(cd* Q, int S, int* state) {
+    __shared__ double red[2 * 8];
+    const long long b = blockIdx.x;
+    if (state[b] != 0) return;
+    const size_t nn = (size_t)S * S;
+    cd* q = Q + b * nn;
+    double tx = 0.0, ty = 0.0;
+    for (int i = threadIdx.x; i < S; i += 256) {
+        tx += q[(size_t)i * S + i].x;
+        ty += q[(size_t)i * S + i].y;
+    }
+    double v[2] = {tx, ty};
+    block_sum<2>(v, red);
+    const double n2 = v[0] * v[0] + v[1] * v[1];
+    const bool ok = n2 > 0.0 && isfinite(n2);
+    const cd inv = ok ? cmake<double>(v[0] / n2, -v[1] / n2) : cmake<double>(0.0, 0.0);
+    for (size_t e = threadIdx.x; e < nn; e += 256) q[e] = cmul(q[e], inv);
+    if (threadIdx.x == 0 && (!ok || 1.0 - v[0] < 1e-13)) state[b] = 1;
+}
+
+// eigenvector = the column of the (nearly rank-one) power with the largest diagonal entry; eigenvalue = its
+// Rayleigh quotient with the ORIGINAL matrix
+__global__ void __launch_bounds__(256) gc_extract_kernel(const float2* csm, const cd* P, int S, float* value,
+                                                          float2* vector) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[2 * 8];
+    __shared__ int best_sh;
+    cd* vec = reinterpret_cast<cd*>(smem_raw);  // [S]
+    const long long b = blockIdx.x;
+    const size_t nn = (size_t)S * S;
+    const cd* p = P + b * nn;
+    const float2* a = csm + b * nn;
+    if (threadIdx.x == 0) {
+        int best = 0;
+        double bv = -1.0;
+        for (int i = 0; i < S; ++i) {
+            const double d = p[(size_t)i * S + i].x;
+            if (d > bv) {
+                bv = d;
+                best = i;
+            }
+        }
+        best_sh = best;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += 256) vec[i] = p[(size_t)i * S + best_sh];
+    __syncthreads();
+    double num = 0.0, den = 0.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = warp; i < S; i += 8) {  // one warp per row of A: coalesced
+        cd acc = cmake<double>(0.0, 0.0);
+        for (int k = lane; k < S; k += 32) {
+            const float2 av = a[(size_t)i * S + k];
+            acc = cadd(acc, cmul(cmake<double>(av.x, av.y), vec[k]));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        }
+        if (lane == 0) {
+            num += vec[i].x * acc.x + vec[i].y * acc.y;
+            den += vec[i].x * vec[i].x + vec[i].y * vec[i].y;
+        }
+    }
+    double v[2] = {num, den};
+    block_sum<2>(v, red);
+    const double lam = v[1] > 0.0 ? v[0] / v[1] : 0.0;
+    const double inv = v[1] > 0.0 ? 1.0 / sqrt(v[1]) : 0.0;
+    if (threadIdx.x == 0) value[b] = (float)lam;
+    for (int i = threadIdx.x; i < S; i += 256)
+        vector[b * S + i] = make_float2((float)(vec[i].x * inv), (float)(vec[i].y * inv));
+}
+
+}  // namespace
+
+int64_t sc_global_coherence_blocked_workspace(int64_t BF, int S) {
+    return 2 * BF * (int64_t)S * S * (int64_t)sizeof(cd) + BF * 4 + 256;
+}
+
+int sc_global_coherence_blocked(const void* csm_c64, int64_t BF, int S, float* out_value, void* out_vector_c64,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
+    if (int rc = check_s(S, "sc_global_coherence")) return rc;
+    const int64_t need = sc_global_coherence_blocked_workspace(BF, S);
+    if (!workspace || workspace_bytes < need) {
+        sc_set_error("sc_global_coherence: workspace of %lld bytes required, got %lld", (long long)need,
+                     (long long)workspace_bytes);
+        return SC_ERR_WORKSPACE;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t mat = (size_t)BF * S * S;
+    cd* P = reinterpret_cast<cd*>(workspace);
+    cd* Q = P + mat;
+    int* state = reinterpret_cast<int*>(Q + mat);
+    const float2* csm = reinterpret_cast<const float2*>(csm_c64);
+    gc_init_kernel<<<(unsigned)BF, 256, 0, st>>>(csm, S, P, state);
+    ZGemmParams g;
+    g.a_so = g.b_so = g.c_so = (long long)S * S;
+    g.a_si = g.b_si = g.c_si = 0;
+    g.n_inner = 1; g.S = S; g.conj_b = 0; g.add_identity = 0; g.state = state; g.passthrough = 1; g.err = nullptr;
+    g.upper_only = 0;
+    for (int it = 0; it < kGcSquarings; ++it) {
+        g.A = P; g.Bm = P; g.C = Q;
+        zb_gemm(g, BF, st);
+        gc_norm_kernel<<<(unsigned)BF, 256, 0, st>>>(Q, S, state);
+        cd* t = P;
+        P = Q;
+        Q = t;
+    }
+    gc_extract_kernel<<<(unsigned)BF, 256, (size_t)S * sizeof(cd), st>>>(csm, P, S, out_value,
+                                                                        reinterpret_cast<float2*>(out_vector_c64));
     SC_LAUNCH_OK();
     return SC_OK;
 }

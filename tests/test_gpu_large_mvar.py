@@ -186,3 +186,20 @@ def test_wilson_diverging_problem_is_flagged_like_the_reference(sc):
     c = sc.Connectivity.from_multitaper(m, output="torch")
     c._mvar(max_iterations=12)
     assert int(c.last_wilson_flags[0]) == 1 and int(c.last_wilson_iterations[0]) == 12
+
+
+@pytest.mark.parametrize("s,n_trials", [(70, 12), (130, 20)])
+def test_global_coherence_large_vs_oracle(sc, s, n_trials):
+    """global_coherence above 64 signals: repeated squaring with the tiled c128 GEMM vs the oracle's SVD."""
+    fs, n = 200.0, 32
+    x = O.synthetic_series(2 * n, n_trials, s, fs, seed=77).astype(np.float32)
+    m = sc.Multitaper(x, sampling_frequency=fs, time_halfbandwidth_product=2, time_window_duration=n / fs)
+    c = sc.Connectivity.from_multitaper(m)
+    val, vec = c.global_coherence()
+    taps = O.dpss_tapers(n, 2, O.default_n_tapers(2), fs)
+    coef = O.multitaper_fft(x.astype(np.float64), fs, taps, n, n, n)
+    ref_val, ref_vec = O.global_coherence(coef)
+    assert val.shape == ref_val.shape and vec.shape == ref_vec.shape
+    assert_parity(val, ref_val, 1e-5, f"global coherence S={s}")
+    overlap = np.abs(np.sum(np.conj(vec) * ref_vec, axis=-2))
+    assert np.allclose(overlap, 1.0, atol=1e-3)
