@@ -74,8 +74,35 @@ def dtf512_section(T, C):
                         row_sums=dtf.sum(axis=-1)[0], col_mean=dtf.mean(axis=-2)[0, ::6])
 
 
+def baseline_configs_section(T, C):
+    """BASELINE.json configs[1] in full (64 ch x 16 trials x 10 s @ 1 kHz, NW 3: power + coherency) and configs[2]
+    on 3 of its 30 windows (128 ch x 32 trials @ 1 kHz, NW 4: expected CSM) through the
+    live reference; float32-representable input (SURVEY.md 8d recipe), only slices are kept."""
+    out = {}
+    x2 = series(20261017 + 2, 10_000, 16, 64, 1000.0).astype(np.float32).astype(np.float64)
+    m = T.Multitaper(x2, sampling_frequency=1000.0, time_halfbandwidth_product=3, time_window_duration=1.0)
+    c = C.Connectivity.from_multitaper(m, blocks=8)
+    power = np.asarray(c.power())
+    coh = np.asarray(c.coherency())
+    assert power.shape == (10, 501, 64) and coh.shape == (10, 501, 64, 64)
+    out["cfg2_power"] = power[::3, ::7]
+    out["cfg2_coherency"] = coh[::3, ::25, :8, :]
+    x3 = series(20261017 + 3, 3_000, 32, 128, 1000.0).astype(np.float32).astype(np.float64)
+    m = T.Multitaper(x3, sampling_frequency=1000.0, time_halfbandwidth_product=4, time_window_duration=1.0)
+    c = C.Connectivity.from_multitaper(m, blocks=16)
+    csm = np.asarray(c._expectation_cross_spectral_matrix())
+    assert csm.shape == (3, 1000, 128, 128)
+    out["cfg3_csm"] = csm[:, ::100, :8, :]
+    # (weighted_phase_lag_index cannot be generated here: with `blocks` the reference's own diagonal masking
+    # raises IndexError (connectivity.py:1015), without blocks the un-averaged CSM of this geometry is 176 GB)
+    np.savez_compressed(os.path.join(HERE, "baseline_configs.npz"), **out)
+
+
 def main():
     T, C, M = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "configs":
+        baseline_configs_section(T, C)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "psi":
         psi_section(T, C)
         return

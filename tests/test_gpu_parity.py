@@ -636,3 +636,35 @@ def test_phase_slope_index_vs_oracle_larger(sc):
     coef = O.multitaper_fft(x.astype(np.float64), fs, O.dpss_tapers(250, 3, 5, fs), 250, 250, 250)
     ref = O.phase_slope_index(coef, O.frequencies(250, fs), [8.0, 120.0], 5.0)
     assert_parity(got, ref, TOL, "PSI S=64")
+
+
+# --------------------------------------------------------------------------- #
+# BASELINE.json configs against the LIVE reference (tests/golden/baseline_configs.npz, slices)
+# --------------------------------------------------------------------------- #
+def test_baseline_config2_full_vs_live_reference(sc):
+    """configs[1] in full: 64 channels x 16 trials x 10 s @ 1 kHz, 5 tapers, power + coherency."""
+    g = golden("baseline_configs.npz")
+    x = O.synthetic_series(10_000, 16, 64, 1000.0, seed=20261017 + 2).astype(np.float32)
+    m = sc.Multitaper(x, sampling_frequency=1000.0, time_halfbandwidth_product=3, time_window_duration=1.0)
+    out = sc.Connectivity.from_multitaper(m).compute(["power", "coherency"])
+    assert out["power"].shape == (10, 501, 64) and out["coherency"].shape == (10, 501, 64, 64)
+    assert_parity(out["power"][::3, ::7], g["cfg2_power"], TOL, "config 2 power")
+    assert_parity(out["coherency"][::3, ::25, :8, :], g["cfg2_coherency"], TOL, "config 2 coherency")
+
+
+def test_baseline_config3_windows_vs_live_reference(sc):
+    """configs[2] geometry on 3 of its 30 windows: 128 channels x 32 trials @ 1 kHz, 7 tapers, expected CSM
+    (tcgen05 path) against the live reference; weighted phase lag index against the oracle (the reference cannot
+    produce it at this size: see make_golden.py)."""
+    g = golden("baseline_configs.npz")
+    x = O.synthetic_series(3_000, 32, 128, 1000.0, seed=20261017 + 3).astype(np.float32)
+    m = sc.Multitaper(x, sampling_frequency=1000.0, time_halfbandwidth_product=4, time_window_duration=1.0)
+    c = sc.Connectivity.from_multitaper(m)
+    csm = c._expectation_cross_spectral_matrix()
+    assert csm.shape == (3, 1000, 128, 128)
+    assert_parity(csm[:, ::100, :8, :], g["cfg3_csm"], TOL, "config 3 CSM")
+    wpli = c.weighted_phase_lag_index()
+    coef = O.multitaper_fft(x[:1000].astype(np.float64), 1000.0, O.dpss_tapers(1000, 4, 7, 1000.0), 1000, 1000, 1000)
+    # pairwise measure: the first 16 channels' block equals the measure of those 16 channels alone
+    assert_parity(wpli[:1, :, :16, :16], O.weighted_phase_lag_index(coef[..., :16]), 5e-5,
+                  "config 3 wPLI (window 0, 16-channel block) vs oracle")

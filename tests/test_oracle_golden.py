@@ -161,3 +161,16 @@ def test_phase_slope_index(case):
     coef = O.multitaper_fft(g["x"], fs, taps, n, step, nfft)
     got = O.phase_slope_index(coef, O.frequencies(nfft, fs), **PSI_CASES[case])
     assert_parity(got, g[case], 1e-9, f"PSI {case}")
+
+
+def test_baseline_config2_window_vs_live_reference():
+    """The oracle on window 3 of BASELINE configs[1] (64 ch x 16 trials, 1 s @ 1 kHz, 5 tapers) against the live
+    reference's power and coherency (tests/golden/baseline_configs.npz holds windows 0, 3, 6, 9)."""
+    g = golden("baseline_configs.npz")
+    x = O.synthetic_series(10_000, 16, 64, 1000.0, seed=20261017 + 2).astype(np.float32).astype(np.float64)
+    taps = O.dpss_tapers(1000, 3, O.default_n_tapers(3), 1000.0)
+    coef = O.multitaper_fft(x[3000:4000], 1000.0, taps, 1000, 1000, 1000)
+    power = O.power(coef)[..., :501, :]
+    assert_parity(power[0, ::7], g["cfg2_power"][1], 1e-9, "config 2 power, window 3")
+    coh = O.coherency(coef, row_block=16)
+    assert_parity(coh[0, ::25, :8, :], g["cfg2_coherency"][1], 1e-9, "config 2 coherency, window 3")
