@@ -98,8 +98,32 @@ def baseline_configs_section(T, C):
     np.savez_compressed(os.path.join(HERE, "baseline_configs.npz"), **out)
 
 
+CFG4_PAIRS = [(0, 1), (2, 5), (10, 200), (3, 255), (100, 101), (17, 18)]
+
+
+def config4_section(T, C):
+    """BASELINE.json configs[3] (the headline workload: 256 ch x 64 trials @ 1 kHz, NW 4 -> 7 tapers, 1 s windows)
+    on ONE window through the live reference: coherence_magnitude and pairwise spectral Granger prediction among
+    the 12 channels that the six pairs below touch.  Both are pairwise measures (a pair's value depends on its two
+    channels only), and the reference cannot evaluate them on all 256 channels here: its subset-Granger path
+    allocates the un-averaged (1, 64, 7, 1000, 256, 256) CSM = 438 GB (connectivity.py:551)."""
+    x = series(20261017 + 4, 1_000, 64, 256, 1000.0).astype(np.float32).astype(np.float64)
+    ij = np.array(CFG4_PAIRS)
+    chans = np.unique(ij)
+    m = T.Multitaper(x[:, :, chans], sampling_frequency=1000.0, time_halfbandwidth_product=4, time_window_duration=1.0)
+    c = C.Connectivity.from_multitaper(m)
+    coh = np.asarray(c.coherence_magnitude())
+    gc = np.asarray(c.pairwise_spectral_granger_prediction())
+    assert coh.shape == (1, 501, chans.size, chans.size) and gc.shape == coh.shape
+    np.savez_compressed(os.path.join(HERE, "config4.npz"), channels=chans, pairs=ij, coherence=coh[0, ::5],
+                        granger=gc[0])
+
+
 def main():
     T, C, M = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "config4":
+        config4_section(T, C)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "configs":
         baseline_configs_section(T, C)
         return
