@@ -40,7 +40,7 @@ constexpr int kZP = kZT + 1;
 
 // C = A op(B) (+ I): 64 x 64 tile per CTA, 256 threads as 16 x 16, 4 x 4 interleaved micro-tile per thread
 // (rows ty + 16 i, columns tx + 16 j: conflict-free 16-byte shared loads, coalesced stores).
-__global__ void __launch_bounds__(256) zb_gemm_kernel(const ZGemmParams p) {
+__global__ void __launch_bounds__(256, 2) zb_gemm_kernel(const ZGemmParams p) {
     __shared__ cd As[2][kZK][kZP];
     __shared__ cd Bs[2][kZK][kZP];
     const int S = p.S;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) zb_panel_kernel(const ZInvParams p) {
 }
 
 // M[i, c] <- (i in J ? 0 : M[i, c]) + sum_k T_J[i, k] RB[k, c]  (c outside J);  M[:, J] <- T_J
-__global__ void __launch_bounds__(256) zb_update_kernel(const ZInvParams p) {
+__global__ void __launch_bounds__(256, 2) zb_update_kernel(const ZInvParams p) {
     __shared__ cd Ts[8][kZP];
     __shared__ cd Rs[8][kZP];
     const int S = p.S, w = p.w, j0 = p.j0;
