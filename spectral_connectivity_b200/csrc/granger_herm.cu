@@ -234,6 +234,129 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
     stat[0] = err2; stat[1] = rest2; stat[2] = c00; stat[3] = c10; stat[4] = c01m; stat[5] = c11m;
 }
 
+// Plus operator on the packed lag sequences of the DEFECT E = G^-1 S G^-H - I (B = 2I + E, [B]+ = I + [E]+):
+// same window as PlusWindow, but lag 0 IS the residual (nothing to subtract).
+struct PlusWindowDefect {
+    float inv_n;
+    float* lag0;
+    __device__ __forceinline__ cx<float> operator()(int bb, int k, cx<float> z) const {
+        if (k == 0) {
+            const float h = 0.5f * inv_n;
+            if (bb == 0) {
+                lag0[0] = z.x * inv_n;
+                lag0[2] = z.y * inv_n;
+                return cmake<float>(z.x * h, z.y * h);
+            }
+            lag0[1] = z.x * inv_n;
+            return cmake<float>(z.x * h, 0.f);
+        }
+        return cmake<float>(z.x * inv_n, z.y * inv_n);
+    }
+};
+
+// Defect-correction form of one fp64 Wilson iteration (mixed-precision mode).  Near the fixed point
+// B = G^-1 S G^-H + I = 2I + E with a small E, and the plus operator is linear with [2I]+ = I, so
+// G P = G + G [E]+.  E is formed per bin in fp64 (the cancellation M - I happens there), but its causal
+// projection -- the four FFTs, i.e. nearly all of the shared-memory traffic -- runs in FP32: an FFT error
+// of 1e-7 RELATIVE TO E (|E| <= 1.5e-3 when fp64 takes over, 1e-6 at the last iteration) moves G by
+// 1e-10 ... 1e-13 relative, far below the 1e-8 stopping tolerance and the float32 output.  Same outputs as
+// herm_iteration<double> (stat[], lag0[] as float).
+template <int FPT, typename FFT>
+__device__ __forceinline__ void herm_iteration_defect(cd (&g00)[FPT], cd (&g01)[FPT], cd (&g10)[FPT], cd (&g11)[FPT],
+                                                      const float (&s00)[FPT], const float (&s11)[FPT],
+                                                      const float2 (&s01)[FPT], cx<float>* ZA, cx<float>* ZB,
+                                                      const ScFftPlan& plan, const cx<float>* tw, int N, int fnn,
+                                                      float* lag0, double (&stat)[6]) {
+#pragma unroll
+    for (int q = 0; q < FPT; ++q) {
+        const int f = threadIdx.x + q * kThreads;
+        if (f < fnn) {
+            const cd det = csub(cmul(g00[q], g11[q]), cmul(g01[q], g10[q]));
+            const double dn = 1.0 / (det.x * det.x + det.y * det.y);
+            const cd idet = cmake<double>(det.x * dn, -det.y * dn);
+            const cd u0 = cmul(g11[q], idet), u1 = cmul(g01[q], idet);
+            const cd v0 = cmul(g10[q], idet), v1 = cmul(g00[q], idet);
+            const double a = (double)s00[q], d = (double)s11[q];
+            const cd c = cmake<double>((double)s01[q].x, (double)s01[q].y);
+            const cd cc = cconj(c);
+            const cd t00 = csub(cscale(u0, a), cmul(u1, cc));
+            const cd t01 = csub(cmul(u0, c), cscale(u1, d));
+            const cd t10 = csub(cmul(v1, cc), cscale(v0, a));
+            const cd t11 = csub(cscale(v1, d), cmul(v0, c));
+            const float e00 = (float)((t00.x * u0.x + t00.y * u0.y) - (t01.x * u1.x + t01.y * u1.y) - 1.0);
+            const float e11 = (float)((t11.x * v1.x + t11.y * v1.y) - (t10.x * v0.x + t10.y * v0.y) - 1.0);
+            const float e01x = (float)(-(t00.x * v0.x + t00.y * v0.y) + (t01.x * v1.x + t01.y * v1.y));
+            const float e01y = (float)(-(t00.y * v0.x - t00.x * v0.y) + (t01.y * v1.x - t01.x * v1.y));
+            const int fm = f == 0 ? 0 : N - f;
+            ZA[f] = cmake<float>(e00, e11);
+            ZA[fm] = cmake<float>(e00, e11);
+            if (f == fm) {
+                ZA[N + f] = cmake<float>(e01x, e01x);
+            } else {
+                ZA[N + f] = cmake<float>(e01x + e01y, e01x + e01y);
+                ZA[N + fm] = cmake<float>(e01x - e01y, e01x - e01y);
+            }
+        }
+    }
+    __syncthreads();
+    const PlusWindowDefect win = {1.0f / (float)N, lag0};
+    const cx<float>* Q;
+    if (FFT::template Fused<float>::value) {
+        Q = FFT::template conv2<float>(ZA, ZB, tw, win);
+    } else {
+        cx<float>* c = FFT::template run2<float>(ZA, ZB, plan, tw, true);
+        cx<float>* o = (c == ZA) ? ZB : ZA;
+        const int kcut = (N + 1) / 2;
+        for (int k = threadIdx.x; k < N; k += kThreads) {
+            cx<float> y1 = cmake<float>(0.f, 0.f), y2 = y1;
+            if (k < kcut) {
+                y1 = win(0, k, c[k]);
+                y2 = win(1, k, c[N + k]);
+            }
+            o[k] = y1;
+            o[N + k] = y2;
+        }
+        __syncthreads();
+        Q = FFT::template run2<float>(o, c, plan, tw, false);
+    }
+    double err2 = 0.0, rest2 = 0.0, c00 = 0.0, c10 = 0.0, c01m = 0.0, c11m = 0.0;
+    const double h00 = 0.5 * (double)lag0[0], h01 = 0.5 * (double)lag0[1], h11 = 0.5 * (double)lag0[2];  // P0 - I
+#pragma unroll
+    for (int q = 0; q < FPT; ++q) {
+        const int f = threadIdx.x + q * kThreads;
+        if (f < fnn) {
+            const int fm = f == 0 ? 0 : N - f;
+            const cx<float> a1 = Q[f], m1 = Q[fm], a2 = Q[N + f], m2 = Q[N + fm];
+            // [E]+ : Y1 = P00 + i P11, Y2 = P01 + i P10 (spectra of real sequences)
+            const cd p00 = cmake<double>(0.5 * ((double)a1.x + m1.x), 0.5 * ((double)a1.y - m1.y));
+            const cd p11 = cmake<double>(0.5 * ((double)a1.y + m1.y), 0.5 * ((double)m1.x - a1.x));
+            const cd p01 = cmake<double>(0.5 * ((double)a2.x + m2.x), 0.5 * ((double)a2.y - m2.y));
+            const cd p10 = cmake<double>(0.5 * ((double)a2.y + m2.y), 0.5 * ((double)m2.x - a2.x));
+            // dG = G [E]+
+            cd d00 = cadd(cmul(g00[q], p00), cmul(g01[q], p10));
+            cd d01 = cadd(cmul(g00[q], p01), cmul(g01[q], p11));
+            cd d10 = cadd(cmul(g10[q], p00), cmul(g11[q], p10));
+            cd d11 = cadd(cmul(g10[q], p01), cmul(g11[q], p11));
+            err2 = fmax(err2, fmax(fmax(d00.x * d00.x + d00.y * d00.y, d01.x * d01.x + d01.y * d01.y),
+                                   fmax(d10.x * d10.x + d10.y * d10.y, d11.x * d11.x + d11.y * d11.y)));
+            c00 = fmax(c00, g00[q].x * g00[q].x + g00[q].y * g00[q].y);
+            c10 = fmax(c10, g10[q].x * g10[q].x + g10[q].y * g10[q].y);
+            c01m = fmax(c01m, g01[q].x * g01[q].x + g01[q].y * g01[q].y);
+            c11m = fmax(c11m, g11[q].x * g11[q].x + g11[q].y * g11[q].y);
+            const cd n00 = cadd(g00[q], d00), n01 = cadd(g01[q], d01), n10 = cadd(g10[q], d10), n11 = cadd(g11[q], d11);
+            // the update with its constant-matrix part G (P0 - I) removed
+            d00.x -= h00 * g00[q].x; d00.y -= h00 * g00[q].y;
+            d10.x -= h00 * g10[q].x; d10.y -= h00 * g10[q].y;
+            d01.x -= h01 * g00[q].x + h11 * g01[q].x; d01.y -= h01 * g00[q].y + h11 * g01[q].y;
+            d11.x -= h01 * g10[q].x + h11 * g11[q].x; d11.y -= h01 * g10[q].y + h11 * g11[q].y;
+            rest2 = fmax(rest2, fmax(fmax(d00.x * d00.x + d00.y * d00.y, d01.x * d01.x + d01.y * d01.y),
+                                     fmax(d10.x * d10.x + d10.y * d10.y, d11.x * d11.x + d11.y * d11.y)));
+            g00[q] = n00; g01[q] = n01; g10[q] = n10; g11[q] = n11;
+        }
+    }
+    stat[0] = err2; stat[1] = rest2; stat[2] = c00; stat[3] = c10; stat[4] = c01m; stat[5] = c11m;
+}
+
 template <int FPT, typename FFT>
 __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -357,8 +480,13 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
             }
             for (int it = it0; it < p.max_iter && !converged; ++it) {
                 double st[6];
-                herm_iteration<double, FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, 1.0, 1.0, 1.0, ZA, ZB, p.plan, tws, N, fnn,
-                                                 lag0_sh, st);
+                const bool defect = p.tw32 && p.mixed;
+                if (defect)
+                    herm_iteration_defect<FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, ZAf, ZBf, p.plan, twsf, N, fnn,
+                                                    lag0f_sh, st);
+                else
+                    herm_iteration<double, FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, 1.0, 1.0, 1.0, ZA, ZB, p.plan, tws, N,
+                                                     fnn, lag0_sh, st);
                 block_maxn_nonneg<6>(st, redd, phase_d);  // also fences ZA/ZB reuse
                 const double err = sqrt(st[0]);
                 it_done = it + 1;
@@ -374,7 +502,9 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                     // The scalar recursion is a chain of dependent fp64 divisions: one warp runs it and
                     // broadcasts the accumulated factor T (the branch is uniform over the CTA).
                     if (threadIdx.x < 32) {
-                        const double e00 = lag0_sh[0], e01 = lag0_sh[1], e11 = lag0_sh[2];
+                        const double e00 = defect ? (double)lag0f_sh[0] : lag0_sh[0];
+                        const double e01 = defect ? (double)lag0f_sh[1] : lag0_sh[1];
+                        const double e11 = defect ? (double)lag0f_sh[2] : lag0_sh[2];
                         const double m00 = 1.0 + e00, m01 = e01, m11 = 1.0 + e11;  // I + e0 (symmetric)
                         double ca = 1.0 + 0.5 * e00, cb = 0.5 * e01, cd_ = 1.0 + 0.5 * e11;  // C = P0 (already applied)
                         double ta = 1.0, tb = 0.0, td = 1.0;                                 // T = product of later P_j
