@@ -111,6 +111,10 @@ int sc_csm(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, float sc
 int sc_csm_simt(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S, float scale, int mode, void* out,
                 void* stream);
 
+/* NaN/Inf scan of the float32 input (the UserWarning of transforms.py:754-774, connectivity.py:340): ORs 1 into
+ * flag[0] (int32, device, zeroed by the caller) when any of the n samples is not finite. */
+int sc_nonfinite_flag(const float* x, int64_t n, int* flag, void* stream);
+
 /* power as the real diagonal of an expected cross-spectral matrix that has been computed anyway
  * (connectivity.py:441-445: E[|X_i|^2] = E[X_i conj X_i]): csm c64 [BF][S][S] -> f32 [BF][S].  Saves the
  * second pass over the coefficients that sc_power needs. */

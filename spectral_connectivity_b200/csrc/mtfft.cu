@@ -331,6 +331,47 @@ __global__ void repack_kernel(const float2* __restrict__ coef, long long W, long
     }
 }
 
+
+
+// NaN/Inf scan of the input (transforms.py:754-774), one pass at HBM rate: flag[0] |= 1 if any sample is non-finite.
+// `head` scalar samples bring the pointer to 16-byte alignment, then float4 loads, then the scalar tail.
+__global__ void nonfinite_kernel(const float* __restrict__ x, long long n, int head, int* flag) {
+    const float4* x4 = reinterpret_cast<const float4*>(x + head);
+    const long long n4 = (n - head) >> 2;
+    int bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldcs(x4 + i);
+        // (v - v) is 0 for finite values and NaN for Inf / NaN
+        const float t = (v.x - v.x) + (v.y - v.y) + (v.z - v.z) + (v.w - v.w);
+        bad |= !(t == 0.f);
+    }
+    if (blockIdx.x == 0) {
+        const long long tail0 = head + (n4 << 2);
+        for (long long i = threadIdx.x; i < head + (n - tail0); i += blockDim.x) {
+            const float v = x[i < head ? i : tail0 + (i - head)];
+            bad |= !(v - v == 0.f);
+        }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+}  // namespace
+
+extern "C" int sc_nonfinite_flag(const float* x, int64_t n, int* flag, void* stream) {
+    SC_CHECK_ARG(flag && n >= 0, "sc_nonfinite_flag: bad argument");
+    if (n == 0) return SC_OK;
+    SC_CHECK_ARG(x && (reinterpret_cast<uintptr_t>(x) & 3) == 0, "sc_nonfinite_flag: x must be a 4-byte aligned pointer");
+    long long head = ((16 - (long long)(reinterpret_cast<uintptr_t>(x) & 15)) & 15) / 4;
+    if (head > n) head = n;
+    long long blocks = (((n - head) >> 2) + 255) / 256;
+    const long long cap = (long long)sc_num_sms() * 16;
+    blocks = blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
+    nonfinite_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n, (int)head, flag);
+    SC_LAUNCH_OK();
+    return SC_OK;
+}
+
+namespace {
 }  // namespace
 
 extern "C" int64_t sc_mt_fft_workspace_bytes(int n, int nfft) {

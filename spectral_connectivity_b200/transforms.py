@@ -9,6 +9,7 @@ The transform itself -- window gather, detrend, taper product, FFT (:1147-1171, 
 """
 from __future__ import annotations
 
+import ctypes
 import warnings
 from logging import getLogger
 
@@ -139,7 +140,7 @@ class Multitaper:
             self._stream_to_device(ts, dev)
         else:
             self.time_series = ts.to(dev, non_blocking=True).to(torch.float32).contiguous()
-            if not bool(torch.isfinite(self.time_series).all()):
+            if not self._all_finite(self.time_series):
                 warnings.warn(self._NONFINITE_MSG, UserWarning, stacklevel=2)
 
         self.sampling_frequency = sampling_frequency
@@ -157,6 +158,16 @@ class Multitaper:
         self._tapers_dev = None
         self._tw = {}
 
+    @staticmethod
+    def _all_finite(x):
+        """transforms.py:754: one device pass (sc_nonfinite_flag) instead of isfinite().all()'s five."""
+        if not x.is_cuda:
+            return bool(torch.isfinite(x).all())
+        flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+        _lib.check(_lib.load().sc_nonfinite_flag(_lib.ptr(x), x.numel(), _lib.ptr(flag), _lib.stream_ptr()),
+                   "sc_nonfinite_flag")
+        return int(flag.item()) == 0
+
     _ASYNC_H2D_BYTES = 256 << 20
     _NONFINITE_MSG = ("Input time_series contains NaN or infinite values. This will produce "
                       "invalid spectral estimates.")
@@ -166,7 +177,8 @@ class Multitaper:
         self._host_src = ts  # keep the host buffer alive until the copies have run
         n_rows = ts.shape[0]
         self.time_series = torch.empty(tuple(ts.shape), dtype=torch.float32, device=dev)
-        self._finite_flag = torch.ones((), dtype=torch.bool, device=dev)
+        self._finite_flag = torch.zeros(1, dtype=torch.int32, device=dev)  # sc_nonfinite_flag ORs 1 into it
+        lib = _lib.load()
         self._h2d_events = []
         copy_stream = _lib.side_stream(dev, "h2d")
         copy_stream.wait_stream(torch.cuda.current_stream(dev))
@@ -179,7 +191,8 @@ class Multitaper:
                     dst.copy_(ts[r0:r1], non_blocking=True)
                 else:
                     dst.copy_(ts[r0:r1].to(dev, non_blocking=True))
-                self._finite_flag &= torch.isfinite(dst).all()
+                _lib.check(lib.sc_nonfinite_flag(_lib.ptr(dst), dst.numel(), _lib.ptr(self._finite_flag),
+                                                 ctypes.c_void_p(copy_stream.cuda_stream)), "sc_nonfinite_flag")
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 self._h2d_events.append((r1, ev))
@@ -200,7 +213,7 @@ class Multitaper:
         if self._finite_flag is not None:
             flag, self._finite_flag = self._finite_flag, None
             self._wait_rows(self.time_series.shape[0])
-            if not bool(flag):
+            if int(flag.item()) != 0:
                 warnings.warn(self._NONFINITE_MSG, UserWarning, stacklevel=3)
             self._h2d_events = None
             self._host_src = None

@@ -691,3 +691,30 @@ def test_baseline_config4_window_vs_live_reference(sc):
     sub = c.subset_pairwise_spectral_granger_prediction([tuple(p) for p in ij])
     loc = np.searchsorted(ch, ij)
     assert_parity(sub[0][:, ij[:, 0], ij[:, 1]], g["granger"][:, loc[:, 0], loc[:, 1]], TOL, "config 4 Granger (subset API)")
+
+
+def test_nonfinite_scan_kernel(sc):
+    """sc_nonfinite_flag (the NaN/Inf warning scan, transforms.py:754-774): every position incl. the unaligned head
+    and the scalar tail, and the warning through both input paths."""
+    from spectral_connectivity_b200 import _lib
+    lib = _lib.load()
+    base = torch.zeros(4099, dtype=torch.float32, device="cuda")
+    for off in (0, 1, 2, 3):
+        for n in (0, 1, 3, 4, 5, 1023, 4090):
+            for pos in ([None] if n == 0 else [None, 0, n // 2, n - 1]):
+                for bad in (float("nan"), float("inf"), -float("inf")):
+                    x = base[off:off + n]
+                    x.zero_()
+                    if pos is not None:
+                        x[pos] = bad
+                    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+                    _lib.check(lib.sc_nonfinite_flag(_lib.ptr(x), n, _lib.ptr(flag), _lib.stream_ptr()), "scan")
+                    assert int(flag.item()) == (0 if pos is None else 1), (off, n, pos, bad)
+    x = np.random.default_rng(0).standard_normal((300, 3, 5))
+    x[17, 1, 2] = np.inf
+    with pytest.warns(UserWarning, match="NaN or infinite"):
+        sc.Multitaper(x, sampling_frequency=100.0, time_window_duration=1.0)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        sc.Multitaper(np.nan_to_num(x, posinf=0.0), sampling_frequency=100.0, time_window_duration=1.0)
