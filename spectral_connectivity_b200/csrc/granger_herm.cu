@@ -26,9 +26,15 @@ constexpr double kTailRest = 32.0;   // closed-form tail once the non-constant p
                                      // kTailRest * tol: those modes converge quadratically, so what is left of
                                      // them after the update is far below tol (measured deviation from the
                                      // reference's own final iterate: 2e-8 relative at 10 * tol)
-constexpr float kSwitch = 1.5e-3f;     // hand over to fp64 once the non-constant part of the update (scaled
-                                     // units, |G'| ~ 1) is below this: the iteration converges quadratically
-                                     // in those modes, so two fp64 iterations then reach 1e-8
+// Hand over from the fp32 phase to the fp64 (defect-correction) phase once the non-constant part of the update
+// (scaled units, |G'| ~ 1) is below kSwitch: the iteration converges quadratically in those modes, so one or two
+// fp64-phase iterations then reach 1e-8.  Measured on config 4 (Granger stage, after the defect-correction form
+// made the fp64-phase iterations cheaper): 1e-4 312 ms, 2e-4 303, 3e-4 300, 5e-4 303, 7e-4 304, 1.5e-3 306,
+// 3e-3 305, 6e-3 312 -- a flat optimum around 3e-4 .. 7e-4.  Overridable at compile time for such sweeps.
+#ifndef SC_GRANGER_KSWITCH
+#define SC_GRANGER_KSWITCH 4e-4f
+#endif
+constexpr float kSwitch = SC_GRANGER_KSWITCH;
 
 #ifndef SC_GRANGER_POW_TWIDDLES
 #define SC_GRANGER_POW_TWIDDLES 0  // stage twiddles as powers of the first one (fewer shared loads, more
