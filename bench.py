@@ -191,6 +191,32 @@ class ClockSampler:
                 "power_w_max": float(max(power)), "samples": len(sm)}
 
 
+class native_stdout_to_stderr:
+    """Route file descriptor 1 to stderr while native libraries initialise (their banners bypass sys.stdout);
+    always restored, and a no-op if the descriptors cannot be duplicated."""
+
+    def __enter__(self):
+        self.saved = None
+        try:
+            sys.stdout.flush()
+            self.saved = os.dup(1)
+            os.dup2(2, 1)
+        except OSError:
+            if self.saved is not None:
+                os.close(self.saved)
+                self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            try:
+                sys.stdout.flush()
+            finally:
+                os.dup2(self.saved, 1)
+                os.close(self.saved)
+        return False
+
+
 def make_recording(wl, seed, device):
     """Same structure as oracle.synthetic_series (noise + lag-1 even->odd coupling + 40 Hz line),
     generated on the device: building 983 M samples with NumPy would take minutes."""
@@ -219,7 +245,10 @@ def run_gpu(args, wl_name, wl):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # keep stdout to the one JSON line: the NCCL communicator setup prints "NCCL version ..." to stdout
+        with native_stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
     _lib.load()
 
     x_dev = make_recording(wl, rank, dev)
