@@ -147,3 +147,29 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "/root/reference" not in src, f
+
+
+def test_bench_keeps_native_banners_off_stdout(tmp_path):
+    """bench.py prints ONE JSON line on stdout: banners that native libraries write to file descriptor 1 while the
+    process group initialises are routed to stderr, and the descriptor is restored even on an exception."""
+    import subprocess
+    import sys
+    script = tmp_path / "fd.py"
+    script.write_text(
+        "import ctypes, json, sys\n"
+        f"sys.path.insert(0, {str(ROOT)!r})\n"
+        "import bench\n"
+        "libc = ctypes.CDLL(None)\n"
+        "with bench.native_stdout_to_stderr():\n"
+        "    libc.puts(b'NATIVE BANNER')\n"
+        "    libc.fflush(None)\n"
+        "try:\n"
+        "    with bench.native_stdout_to_stderr():\n"
+        "        raise RuntimeError('boom')\n"
+        "except RuntimeError:\n"
+        "    pass\n"
+        "print(json.dumps({'ok': 1}))\n")
+    res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout.strip() == '{"ok": 1}'
+    assert "NATIVE BANNER" in res.stderr
