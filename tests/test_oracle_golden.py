@@ -174,3 +174,17 @@ def test_baseline_config2_window_vs_live_reference():
     assert_parity(power[0, ::7], g["cfg2_power"][1], 1e-9, "config 2 power, window 3")
     coh = O.coherency(coef, row_block=16)
     assert_parity(coh[0, ::25, :8, :], g["cfg2_coherency"][1], 1e-9, "config 2 coherency, window 3")
+
+
+def test_baseline_config4_window_vs_live_reference():
+    """The oracle on the headline workload's geometry (configs[3]: 64 trials x 7 tapers, 1 s @ 1 kHz) for the 12 channels
+    kept in tests/golden/config4.npz: coherence and pairwise spectral Granger against the live reference."""
+    g = golden("config4.npz")
+    ch = g["channels"]
+    x = O.synthetic_series(1_000, 64, 256, 1000.0, seed=20261017 + 4).astype(np.float32).astype(np.float64)[:, :, ch]
+    taps = O.dpss_tapers(1000, 4, O.default_n_tapers(4), 1000.0)
+    coef = O.multitaper_fft(x, 1000.0, taps, 1000, 1000, 1000)
+    coh = O.coherence_magnitude(coef)
+    assert_parity(coh[0, ::5], g["coherence"], 1e-9, "config 4 coherence")
+    gc = O.pairwise_granger(O.expected_csm(coef), O.power(coef))
+    assert_parity(gc[0], g["granger"], 1e-8, "config 4 pairwise Granger")
