@@ -264,8 +264,8 @@ struct PlusWindowDefect {
 // B = G^-1 S G^-H + I = 2I + E with a small E, and the plus operator is linear with [2I]+ = I, so
 // G P = G + G [E]+.  E is formed per bin in fp64 (the cancellation M - I happens there), but its causal
 // projection -- the four FFTs, i.e. nearly all of the shared-memory traffic -- runs in FP32: an FFT error
-// of 1e-7 RELATIVE TO E (|E| <= 1.5e-3 when fp64 takes over, 1e-6 at the last iteration) moves G by
-// 1e-10 ... 1e-13 relative, far below the 1e-8 stopping tolerance and the float32 output.  Same outputs as
+// of 1e-7 RELATIVE TO E (|E| <~ 1e-3 when fp64 takes over, 1e-6 at the last iteration) moves G by ~1e-10
+// absolute, two orders below the 1e-8 stopping tolerance and far below the float32 output.  Same outputs as
 // herm_iteration<double> (stat[], lag0[] as float).
 template <int FPT, typename FFT>
 __device__ __forceinline__ void herm_iteration_defect(cd (&g00)[FPT], cd (&g01)[FPT], cd (&g10)[FPT], cd (&g11)[FPT],
