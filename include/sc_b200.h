@@ -69,6 +69,14 @@ extern "C" {
 int sc_version(void);
 const char* sc_last_error(void);
 
+/* Measurement aid (bench.py roofline denominators; SURVEY.md section 8d asks for the Wilson stage against the
+ * FP32 / FP64 vector peak, which MEASURED_PEAKS.json does not hold): launches one kernel of dependent-chain FMAs,
+ * 8 independent chains per thread, every SM fully occupied.  dtype 0 = float32, 1 = float64.  *out_flops (host)
+ * receives the number of floating-point operations the launch performs (2 per FMA); the caller times the launch
+ * with CUDA events on ``stream``.  scratch: device buffer of at least sc_simt_peak_scratch_bytes() bytes. */
+int sc_simt_peak(int dtype, int fma_per_chain, void* scratch, double* out_flops /* host */, void* stream);
+int64_t sc_simt_peak_scratch_bytes(void);
+
 /* Multitaper.fft() -- transforms.py:1147-1171: sliding-window gather (:1311-1374),
  * detrend (:1798-1915), DPSS taper product + FFT(n=nfft)/fs (:1377-1405), fused.
  *  x        float32 (N,T,S), S fastest
@@ -155,16 +163,20 @@ int sc_wilson2(const void* csm_c128, int64_t B, int nfft, double tolerance, int 
  *           the lag-0 coefficient and then zeroes the lower triangle, mpd.py:132-138, so the lag-0
  *           off-diagonal residual halves per iteration), the remaining iterations are summed in
  *           closed form up to the iterate the reference stops at; out_iters reports that iterate.
- *  mixed_precision  1 (hermitian_half only, needs twiddle_c64 = c64 [nfft]): the first iterations, while
- *           max|dG| is still above 2e-3 of |G|, run in fp32 on the row-scaled problem; every later
+ *  mixed_precision  1 (hermitian_half only, needs twiddle_c64 = c64 [nfft]): the first iterations, while the
+ *           non-constant part of the update is still above 4e-4 of |G|, run in fp32 on the row-scaled problem; every later
  *           iteration, the stopping test and the Granger epilogue are fp64.  Moves the result by
  *           ~5e-7 relative (the fp32-born CSM already carries 3e-7).  0: fp64 throughout.
- *  out_iters/out_flags  int32 [n_pairs][B] or NULL */
+ *  out_iters/out_flags  int32 [n_pairs][B] or NULL
+ *  out_exec_counters  uint64 [4] (device, accumulated with atomicAdd -- the caller zeroes it) or NULL: work the
+ *           hermitian_half kernel actually EXECUTED, summed over all problems: [0] fp32-phase iterations,
+ *           [1] fp64-phase iterations, [2] closed-form tail steps, [3] problems.  out_iters reports the
+ *           reference-equivalent iteration count instead (= [0]+[1]+[2] summed).  Used for roofline accounting. */
 int sc_granger_pairwise(const void* csm_c64, const float* power, int64_t B, int F, int nfft, int hermitian_half,
                         int64_t S, const int* pairs, int64_t n_pairs, double tolerance, int max_iterations,
                         int tail_extrapolation, int mixed_precision, const void* twiddle_c128,
-                        const void* twiddle_c64, float* out_gc, int* out_iters, int* out_flags, void* workspace,
-                        int64_t workspace_bytes, void* stream);
+                        const void* twiddle_c64, float* out_gc, int* out_iters, int* out_flags,
+                        uint64_t* out_exec_counters, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t sc_wilson_workspace_bytes(int nfft);
 
 /* minimum_phase_decomposition for S x S matrices, 1 <= S <= 1024 (minimum_phase_decomposition.py:227-322):

@@ -524,13 +524,17 @@ def canonical_coherence(coef, group_labels):
     return out, labels
 
 
-def global_coherence(coef):
-    """Largest eigenvalue of the per-(window, frequency) cross-spectral matrix = top singular value
-    squared / n_observations, over ALL Nfft bins, and its eigenvector (defined up to a phase)
-    (connectivity.py:822-895, 2245-2279 with max_rank = 1)."""
+def global_coherence(coef, max_rank=1):
+    """The ``max_rank`` largest eigenvalues of the per-(window, frequency) cross-spectral matrix = singular values
+    squared / n_observations, over ALL Nfft bins, and their eigenvectors (each defined up to a phase)
+    (connectivity.py:822-895, 2245-2279).  Ordering as the reference produces it: descending from the dense SVD
+    when max_rank >= n_signals - 1 (:2258-2266), ASCENDING from scipy's ``svds`` otherwise (:2267-2276)."""
     x = _obs_matrix(coef)
     u, sv, _ = np.linalg.svd(x, full_matrices=False)
-    return sv[..., :1] ** 2 / x.shape[-1], u[..., :, :1]
+    val, vec = sv[..., :max_rank] ** 2 / x.shape[-1], u[..., :, :max_rank]
+    if max_rank < x.shape[-2] - 1:
+        val, vec = val[..., ::-1], vec[..., :, ::-1]
+    return val, vec
 
 
 # --------------------------------------------------------------------------- #

@@ -32,7 +32,9 @@ SIGNATURES = {
     "sc_phase_slope_index": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int, _P, _P]),
     "sc_wilson2": (c_int, [_P, c_int64, c_int, c_double, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
     "sc_granger_pairwise": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int64, _P, c_int64, c_double, c_int,
-                                    c_int, c_int, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+                                    c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "sc_simt_peak": (c_int, [c_int, c_int, _P, ctypes.POINTER(c_double), _P]),
+    "sc_simt_peak_scratch_bytes": (c_int64, []),
     "sc_wilson_workspace_bytes": (c_int64, [c_int]),
     "sc_wilson": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, c_double, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
     "sc_wilson_general_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),

@@ -43,7 +43,12 @@ _PAIRWISE = {
     "debiased_squared_phase_lag_index": ("pli", _lib.M_DPLI2, False),
     "debiased_squared_weighted_phase_lag_index": ("pli", _lib.M_DWPLI2, False),
 }
-_GRANGER_OK = ("trials_tapers", "time_trials", "time_tapers", "time_trials_tapers")
+# Every expectation type is factorised; the reference couples the Wilson freeze / convergence test across the leading
+# axis of the CSM (minimum_phase_decomposition.py:290, 310-315: several kept tapers of one window, or -- for
+# 'time_trials_tapers' -- single frequency bins), the device treats every kept index as its own problem: results differ
+# by O(tolerance) = 1e-8 absolute (tests/test_gpu_round2.py::test_granger_and_dtf_every_expectation_type, 1e-5 vs
+# the live reference).
+_GRANGER_OK = tuple(EXPECTATION_AXES)
 MEASURES = ("power", "expectation_cross_spectral_matrix", "_phase_locking_value",
             "pairwise_spectral_granger_prediction") + tuple(_PAIRWISE)
 
@@ -76,7 +81,7 @@ class Connectivity:
 
     def __init__(self, fourier_coefficients, expectation_type="trials_tapers", frequencies=None,
                  time=None, blocks=None, dtype=np.complex128, *, output="numpy",
-                 max_chunk_bytes=4 << 30, reduce_group=None, _multitaper=None):
+                 max_chunk_bytes=4 << 30, reduce_group=None, reduce_mode="all_reduce", _multitaper=None):
         src = getattr(fourier_coefficients, "_sc_source", None)
         if (_multitaper is None and src is not None and isinstance(fourier_coefficients, torch.Tensor)
                 and fourier_coefficients._version == src[1]):
@@ -97,6 +102,8 @@ class Connectivity:
             raise ValueError(_expectation_error(expectation_type))
         if output not in ("numpy", "torch"):
             raise ValueError("output must be 'numpy' or 'torch'")
+        if reduce_mode not in ("all_reduce", "reduce_scatter"):
+            raise ValueError("reduce_mode must be 'all_reduce' or 'reduce_scatter'")
         if not torch.cuda.is_available():
             raise RuntimeError("spectral_connectivity_b200 needs a CUDA device; there is no CPU fallback.")
         self._device = torch.device("cuda", torch.cuda.current_device())
@@ -125,9 +132,35 @@ class Connectivity:
         self._output = output
         self._max_chunk_bytes = int(max_chunk_bytes)
         self._reduce_group = reduce_group
+        self._reduce_mode = reduce_mode
         self.time = time if not isinstance(time, torch.Tensor) else time.cpu().numpy()
+        self.owned_windows = None  # reduce_scatter mode: global indices of the windows this rank's results hold
+        self._group_state = None
+        if reduce_group is not None:
+            self._agree_with_group()
         self.last_granger_iterations = None
         self.last_granger_flags = None
+        self.last_granger_executed = None
+
+    def _agree_with_group(self):
+        """Ranks of ``reduce_group`` hold disjoint OBSERVATION shards (e.g. trials) of the same windows.  Everything
+        the collectives depend on must be identical on every rank, so it is agreed once here: the global observation
+        counts (shards may be unequal: array_split of 8 trials over 3 ranks), the window-chunk size (from the
+        largest per-window footprint in the group) and the conjugate-symmetry flag (AND over ranks)."""
+        import torch.distributed as dist
+
+        from .distributed import agree
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        local_obs = int(np.prod([self._shape[a] for a in EXPECTATION_AXES[self.expectation_type]]))
+        row = [n_win, nfft, n_sig, local_obs, n_trials * n_tapers, n_trials * n_tapers * n_sig * 8,
+               1 if self._hermitian else 0]
+        world = dist.get_world_size(self._reduce_group)
+        self._group_state = agree(self._reduce_group, row, self._device,
+                                  0 in EXPECTATION_AXES[self.expectation_type])
+        self._hermitian = self._group_state.hermitian
+        if self._reduce_mode == "reduce_scatter" and world > 1:
+            from .distributed import owned_windows
+            self.owned_windows = owned_windows(self._chunk_bounds(nfft, "trials_tapers"), world, self._group_state.rank)
 
     @staticmethod
     def _is_conjugate_symmetric(coef, rtol=1e-6):
@@ -180,11 +213,9 @@ class Connectivity:
     @property
     def n_observations(self):
         """connectivity.py:594-610."""
-        n = int(np.prod([self._shape[a] for a in EXPECTATION_AXES[self.expectation_type]]))
-        if self._reduce_group is not None:
-            import torch.distributed as dist
-            n *= dist.get_world_size(self._reduce_group)
-        return n
+        if self._group_state is not None:
+            return self._group_state.n_observations  # sum over the ranks' (possibly unequal) shards
+        return int(np.prod([self._shape[a] for a in EXPECTATION_AXES[self.expectation_type]]))
 
     def _finish(self, t):
         if self._output == "torch":
@@ -196,52 +227,202 @@ class Connectivity:
         return host.numpy()
 
     # ---- streaming engine ----------------------------------------------------------
-    def _chunks(self, n_freq, expectation_type=None):
-        """Yield (b0, b1, planar chunk [b1-b0][n_freq][2][R][S], R)."""
-        lib = _lib.load()
-        expectation_type = expectation_type or self.expectation_type
+    def _scatter(self, expectation_type=None):
+        """True when results are window-sharded over the reduce group (reduce_scatter along the window axis)."""
+        gs = self._group_state
+        et = expectation_type or self.expectation_type
+        return (gs is not None and gs.world > 1 and self._reduce_mode == "reduce_scatter"
+                and 0 not in EXPECTATION_AXES[et])
+
+    def _chunk_bounds(self, n_freq, expectation_type=None):
+        from .distributed import plan_window_chunks
+        et = expectation_type or self.expectation_type
         n_win, n_trials, n_tapers, nfft, n_sig = self._shape
-        time_kept = 0 not in EXPECTATION_AXES[expectation_type]
-        if time_kept:
+        if 0 in EXPECTATION_AXES[et]:
+            return [(0, n_win)]
+        gs = self._group_state
+        if gs is None or gs.world == 1:
             per_window = n_trials * n_tapers * n_freq * n_sig * 8
-            wc = max(1, min(n_win, self._max_chunk_bytes // max(per_window, 1)))
+            return plan_window_chunks(n_win, per_window, self._max_chunk_bytes, shrink_tail=self._output == "numpy")
+        # reduce group: every rank must derive the same bounds -> only group-agreed numbers; the chunk is also the
+        # granularity of the collective, so the reduced sums (CSM: S^2 * 8 bytes per window and bin) count too.
+        # Sized for all nfft bins whatever ``n_freq`` is streamed, so that the window ownership under
+        # reduce_scatter is one fixed property of the object (``owned_windows``), not of the measure.
+        per_window = max(gs.per_window_bin_bytes * nfft, nfft * n_sig * n_sig * 8)
+        return plan_window_chunks(n_win, per_window, min(self._max_chunk_bytes, 2 << 30), world=gs.world,
+                                  multiple_of_world=self._scatter(et))
+
+    def _owned(self, n_freq, expectation_type=None):
+        """reduce_scatter mode: how many windows this rank's results hold (else None = all)."""
+        if not self._scatter(expectation_type):
+            return None
+        return len(self.owned_windows)
+
+    def _kept_dims(self, expectation_type=None, n_local_windows=None):
+        et = expectation_type or self.expectation_type
+        dims = []
+        for a in range(3):
+            if a in EXPECTATION_AXES[et]:
+                continue
+            dims.append(self._shape[a] if a != 0 or n_local_windows is None else n_local_windows)
+        return tuple(dims)
+
+    def _coefficients_chunk(self, w0, w1, n_freq, expectation_type):
+        """Planar coefficients [nb][n_freq][2][R][S] of windows [w0, w1) for the expectation type -> (xp, nb, R)."""
+        lib = _lib.load()
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        mapping, kept, nb, nr = expectation_map((w1 - w0, n_trials, n_tapers), expectation_type)
+        xp = torch.empty((nb, n_freq, 2, nr, n_sig), dtype=torch.float32, device=self._device)
+        if self._mt is not None:
+            self._mt._transform(xp, _lib.LAYOUT_PLANAR, n_freq, w0, w1 - w0, 0, mapping, nr)
         else:
-            wc = n_win
-        # window ranges: full chunks, then (host output only) a geometrically shrinking tail so that the last
-        # device->host copy, which nothing can overlap, is small
-        bounds, w0 = [], 0
-        while w0 < n_win:
-            left = n_win - w0
-            size = min(wc, left)
-            if self._output == "numpy" and time_kept and left <= wc and left > 1:
-                size = (left + 1) // 2
-            bounds.append((w0, w0 + size))
-            w0 += size
-        for w0, w1 in bounds:
-            mapping, kept, nb, nr = expectation_map((w1 - w0, n_trials, n_tapers), expectation_type)
-            xp = torch.empty((nb, n_freq, 2, nr, n_sig), dtype=torch.float32, device=self._device)
-            if self._mt is not None:
-                self._mt._transform(xp, _lib.LAYOUT_PLANAR, n_freq, w0, w1 - w0, 0, mapping, nr)
+            rc = lib.sc_repack_coefficients(_lib.ptr(self._coef[w0:w1]), w1 - w0, n_trials, n_tapers,
+                                            nfft, n_sig, n_freq, _lib.map6(mapping), nr, _lib.ptr(xp),
+                                            _lib.stream_ptr())
+            _lib.check(rc, "sc_repack_coefficients")
+        return xp, nb, nr
+
+    def _reduced(self, n_freq, kinds, expectation_type=None, scale=None):
+        """Stream window chunks and yield the expectation sums of each: dict(o0, o1, w0, w1, csm, power, plv, pli)
+        -- tensors hold rows [o0, o1) of THIS rank's output batch axis (``kinds`` selects which are produced;
+        "power" comes from the CSM diagonal when the CSM is produced anyway).
+
+        With a reduce group the partial sums of chunk c are summed over the ranks on a side stream
+        (reduce_scatter along the window axis, or all_reduce) while the main stream already runs the FFT + CSM of
+        chunk c+1; the consumer's epilogues / Wilson factorisations of chunk c then wait for the collective only."""
+        import torch.distributed as dist
+
+        from .distributed import scatter_ownership
+        lib = _lib.load()
+        et = expectation_type or self.expectation_type
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        dev = self._device
+        gs = self._group_state
+        reduce = gs is not None and gs.world > 1
+        scatter = self._scatter(et)
+        time_kept = 0 not in EXPECTATION_AXES[et]
+        if scale is None:
+            scale = 1.0 / self.n_observations
+        comm = _lib.side_stream(dev, "comm") if reduce else None
+        st = _lib.stream_ptr()
+        kinds = set(kinds)
+        want_power = "power" in kinds
+        sums = [k for k in ("csm", "plv", "pli") if k in kinds]
+        if want_power and "csm" not in kinds:
+            sums.append("power")
+
+        def partial_sums(w0, w1):
+            xp, nb, nr = self._coefficients_chunk(w0, w1, n_freq, et)
+            bw = nb // (w1 - w0) if time_kept else nb        # batch rows per window
+            rows = nb
+            if scatter:
+                q, lo, hi = scatter_ownership(w1 - w0, gs.world, gs.rank)
+                rows = q * gs.world * bw                     # padded so that every rank receives q windows
+            item = dict(w0=w0, w1=w1, nb=nb, bw=bw, rows=rows)
+
+            def alloc(shape_tail, dtype, lead=None):
+                t = torch.empty(((rows,) if lead is None else (lead, rows)) + shape_tail, dtype=dtype, device=dev)
+                if rows > nb:
+                    (t[nb:] if lead is None else t[:, nb:]).zero_()
+                return t
+            for kind in sums:
+                if kind == "csm":
+                    t = alloc((n_freq, n_sig, n_sig), torch.complex64)
+                    with _lib.timed("csm"):
+                        _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(t), st),
+                                   "sc_csm")
+                elif kind == "plv":
+                    t = alloc((n_freq, n_sig, n_sig), torch.complex64)
+                    with _lib.timed("plv"):
+                        _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_PLV, _lib.ptr(t), st),
+                                   "sc_csm[plv]")
+                elif kind == "pli":
+                    if rows > nb:   # the kernel writes 4 planes of nb rows: compute compact, then pad
+                        c = torch.empty((4, nb, n_freq, n_sig, n_sig), dtype=torch.float32, device=dev)
+                    else:
+                        c = torch.empty((4, rows, n_freq, n_sig, n_sig), dtype=torch.float32, device=dev)
+                    with _lib.timed("pli"):
+                        _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_PLI, _lib.ptr(c), st),
+                                   "sc_csm[pli]")
+                    if rows > nb:
+                        t = alloc((n_freq, n_sig, n_sig), torch.float32, lead=4)
+                        t[:, :nb] = c
+                    else:
+                        t = c
+                else:
+                    t = alloc((n_freq, n_sig), torch.float32)
+                    with _lib.timed("power"):
+                        _lib.check(lib.sc_power(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.ptr(t), st), "sc_power")
+                item[kind] = t
+            return item
+
+        def enqueue_collective(item):
+            ev = torch.cuda.Event()
+            ev.record()
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm), _lib.timed("collective"):
+                for kind in sums:
+                    t = item[kind]
+                    if not scatter:
+                        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._reduce_group)
+                        continue
+                    own = item["rows"] // gs.world
+                    if kind == "pli":
+                        r = torch.empty((4, own) + tuple(t.shape[2:]), dtype=t.dtype, device=dev)
+                        for a in range(4):
+                            dist.reduce_scatter_tensor(r[a], t[a], op=dist.ReduceOp.SUM, group=self._reduce_group)
+                    else:
+                        r = torch.empty((own,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+                        dist.reduce_scatter_tensor(r, t, op=dist.ReduceOp.SUM, group=self._reduce_group)
+                    item[kind + "_partial"] = t      # keep the send buffer alive until the consumer has run
+                    item[kind] = r
+                done = torch.cuda.Event()
+                done.record(comm)
+            item["done"] = done
+
+        state = dict(o=0)
+
+        def finish(item):
+            if "done" in item:
+                torch.cuda.current_stream().wait_event(item["done"])
+            nb, bw = item["nb"], item["bw"]
+            if scatter:
+                q, lo, hi = scatter_ownership(item["w1"] - item["w0"], gs.world, gs.rank)
+                valid = (hi - lo) * bw
+                item["w0"], item["w1"] = item["w0"] + lo, item["w0"] + hi
+                o0 = state["o"]
             else:
-                rc = lib.sc_repack_coefficients(_lib.ptr(self._coef[w0:w1]), w1 - w0, n_trials, n_tapers,
-                                                nfft, n_sig, n_freq, _lib.map6(mapping), nr, _lib.ptr(xp),
-                                                _lib.stream_ptr())
-                _lib.check(rc, "sc_repack_coefficients")
-            bw = nb // (w1 - w0) if time_kept else nb
-            b0 = w0 * bw if time_kept else 0
-            yield b0, b0 + nb, xp, nr
+                valid = nb
+                o0 = item["w0"] * bw if time_kept else 0
+            for kind in sums:
+                t = item[kind]
+                item[kind] = t[:, :valid] if kind == "pli" else t[:valid]
+            item["o0"], item["o1"] = o0, o0 + valid
+            state["o"] = o0 + valid
+            if want_power and "csm" in kinds:
+                power = torch.empty((valid, n_freq, n_sig), dtype=torch.float32, device=dev)
+                if valid:
+                    with _lib.timed("power"):  # the diagonal of the CSM: no second pass over the coefficients
+                        _lib.check(lib.sc_power_from_csm(_lib.ptr(item["csm"]), valid * n_freq, n_sig, _lib.ptr(power), st),
+                                   "sc_power_from_csm")
+                item["power"] = power
+            return item
 
-    def _kept_dims(self):
-        return tuple(self._shape[a] for a in range(3) if a not in EXPECTATION_AXES[self.expectation_type])
-
-    def _allreduce(self, t):
-        if self._reduce_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._reduce_group)
-        return t
+        pending = None
+        for w0, w1 in self._chunk_bounds(n_freq, et):
+            item = partial_sums(w0, w1)
+            if reduce:
+                enqueue_collective(item)
+                if pending is not None:
+                    yield finish(pending)
+                pending = item
+            else:
+                yield finish(item)
+        if pending is not None:
+            yield finish(pending)
 
     def compute(self, measures, pairs=None, tolerance=1e-8, max_iterations=60, tail_extrapolation=True,
-                mixed_precision=True):
+                mixed_precision=True, out=None):
         """Compute several measures in ONE streaming pass over window chunks.
 
         ``measures``: iterable of names from ``MEASURES``.  Returns {name: array}.  Per chunk
@@ -252,8 +433,14 @@ class Connectivity:
         reference's Wilson iteration in closed form instead of iterating through it -- same
         stopping iterate, same iteration count, results equal to ~1e-7 relative.
         ``False`` runs every iteration like the reference.  ``mixed_precision`` (same path): the
-        first Wilson iterations (update still > 2e-3 of |G|) run in fp32, the rest in fp64; moves
-        results by ~5e-7 relative.  ``False`` keeps the factorisation in fp64 throughout."""
+        first Wilson iterations (non-constant part of the update still > 4e-4 of |G|) run in fp32, the rest in
+        fp64; moves results by ~5e-7 relative.  ``False`` keeps the factorisation in fp64 throughout
+        (``dtype=np.complex128`` at construction does not change this default: see ``Connectivity``).
+
+        ``out`` (output="numpy" only): {name: pinned host array from ``pinned_empty``} to receive results, so that
+        a pipeline calling ``compute`` repeatedly does not allocate (and page-lock) gigabytes per call.
+
+        With ``reduce_mode="reduce_scatter"`` the results hold this rank's windows only (``owned_windows``)."""
         lib = _lib.load()
         measures = list(measures)
         for name in measures:
@@ -269,10 +456,9 @@ class Connectivity:
                 ":313-315); only " + ", ".join(_GRANGER_OK) + " are supported.")
         two_sided = want_granger and not self._hermitian
         n_freq = nfft if two_sided else fnn
-        kept = self._kept_dims()
+        kept = self._kept_dims(n_local_windows=self._owned(n_freq))
         n_batch = int(np.prod(kept)) if kept else 1
         dev = self._device
-        scale = 1.0 / self.n_observations
         needs = set()
         for name in measures:
             if name in _PAIRWISE:
@@ -281,19 +467,20 @@ class Connectivity:
             needs.add("plv")
         if want_granger or "expectation_cross_spectral_matrix" in measures:
             needs.add("csm")
-        need_power = want_granger or "power" in measures or any(
-            m in measures for m in ("coherency", "coherence_magnitude", "coherence_phase", "imaginary_coherence"))
+        if want_granger or "power" in measures or any(
+                m in measures for m in ("coherency", "coherence_magnitude", "coherence_phase", "imaginary_coherence")):
+            needs.add("power")
 
-        out = {}
+        res = {}
         for name in measures:
             if name == "power":
-                out[name] = torch.empty((n_batch, n_freq, n_sig), dtype=torch.float32, device=dev)
+                res[name] = torch.empty((n_batch, n_freq, n_sig), dtype=torch.float32, device=dev)
             elif name == "pairwise_spectral_granger_prediction":
-                out[name] = torch.full((n_batch, fnn, n_sig, n_sig), float("nan"), dtype=torch.float32, device=dev)
+                res[name] = torch.full((n_batch, fnn, n_sig, n_sig), float("nan"), dtype=torch.float32, device=dev)
             elif name in ("expectation_cross_spectral_matrix", "_phase_locking_value", "coherency"):
-                out[name] = torch.empty((n_batch, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
+                res[name] = torch.empty((n_batch, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
             else:
-                out[name] = torch.empty((n_batch, n_freq, n_sig, n_sig), dtype=torch.float32, device=dev)
+                res[name] = torch.empty((n_batch, n_freq, n_sig, n_sig), dtype=torch.float32, device=dev)
 
         pair_t = None
         n_pairs = n_sig * (n_sig - 1) // 2
@@ -312,74 +499,61 @@ class Connectivity:
             tw64 = twiddles(nfft, torch.complex64, dev)
             it_all = torch.zeros((n_pairs, n_batch), dtype=torch.int32, device=dev)
             fl_all = torch.zeros((n_pairs, n_batch), dtype=torch.int32, device=dev)
+            # executed work (fp32 iterations, fp64 iterations, closed-form tail steps, problems): roofline accounting
+            exec_cnt = torch.zeros(4, dtype=torch.int64, device=dev)
 
         # output="numpy": stream each finished chunk to pinned host memory on a side stream while the
         # next chunk computes
         host, copy_stream = {}, None
         if self._output == "numpy":
             copy_stream = _lib.side_stream(dev, "d2h")
-            for name, t in out.items():
+            for name, t in res.items():
                 shp = (t.shape[0], fnn) + tuple(t.shape[2:])
-                host[name] = torch.empty(shp, dtype=t.dtype, pin_memory=True)
+                given = None if out is None else out.get(name)
+                if given is not None:
+                    g = given if isinstance(given, torch.Tensor) else torch.from_numpy(given)
+                    if g.numel() != int(np.prod(shp)) or g.dtype != t.dtype or not g.is_contiguous():
+                        raise ValueError(f"out['{name}'] must be a contiguous {t.dtype} array with {int(np.prod(shp))} "
+                                         f"elements (shape {kept + shp[1:]})")
+                    host[name] = g.reshape(shp)
+                else:
+                    host[name] = torch.empty(shp, dtype=t.dtype, pin_memory=True)
+        elif out is not None:
+            raise ValueError("out= is for output='numpy'; with output='torch' results stay on the device")
 
         def offload(name, b0, b1):
-            if copy_stream is None:
+            if copy_stream is None or b1 <= b0:
                 return
             ev = torch.cuda.Event()
             ev.record()
             copy_stream.wait_event(ev)
             with torch.cuda.stream(copy_stream):
-                host[name][b0:b1].copy_(out[name][b0:b1, :fnn], non_blocking=True)
+                host[name][b0:b1].copy_(res[name][b0:b1, :fnn], non_blocking=True)
 
         st = _lib.stream_ptr()
-        for b0, b1, xp, nr in self._chunks(n_freq):
+        for item in self._reduced(n_freq, needs):
+            b0, b1 = item["o0"], item["o1"]
             nb = b1 - b0
-            power = csm = None
-            if "csm" in needs:
-                csm = torch.empty((nb, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
-                with _lib.timed("csm"):
-                    _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(csm), st),
-                               "sc_csm")
-                self._allreduce(csm)
-                if "expectation_cross_spectral_matrix" in out:
-                    out["expectation_cross_spectral_matrix"][b0:b1] = csm
-                    offload("expectation_cross_spectral_matrix", b0, b1)
-            if need_power:
-                power = torch.empty((nb, n_freq, n_sig), dtype=torch.float32, device=dev)
-                with _lib.timed("power"):
-                    if csm is not None:  # the diagonal of the CSM: no second pass over the coefficients
-                        _lib.check(lib.sc_power_from_csm(_lib.ptr(csm), nb * n_freq, n_sig, _lib.ptr(power), st),
-                                   "sc_power_from_csm")
-                    else:
-                        _lib.check(lib.sc_power(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.ptr(power), st),
-                                   "sc_power")
-                        self._allreduce(power)
-                if "power" in out:
-                    out["power"][b0:b1] = power
-                    offload("power", b0, b1)
-            plv = pli = None
-            if "plv" in needs:
-                plv = torch.empty((nb, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
-                with _lib.timed("plv"):
-                    _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_PLV, _lib.ptr(plv), st),
-                               "sc_csm[plv]")
-                self._allreduce(plv)
-                if "_phase_locking_value" in out:
-                    out["_phase_locking_value"][b0:b1] = plv
-                    offload("_phase_locking_value", b0, b1)
-            if "pli" in needs:
-                pli = torch.empty((4, nb, n_freq, n_sig, n_sig), dtype=torch.float32, device=dev)
-                with _lib.timed("pli"):
-                    _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_PLI, _lib.ptr(pli), st),
-                               "sc_csm[pli]")
-                self._allreduce(pli)
-            del xp
+            if nb == 0:
+                continue
+            csm, power, plv, pli = item.get("csm"), item.get("power"), item.get("plv"), item.get("pli")
+            if "expectation_cross_spectral_matrix" in res:
+                res["expectation_cross_spectral_matrix"][b0:b1] = csm
+                offload("expectation_cross_spectral_matrix", b0, b1)
+            if "power" in res:
+                res["power"][b0:b1] = power
+                offload("power", b0, b1)
+            if "_phase_locking_value" in res:
+                res["_phase_locking_value"][b0:b1] = plv
+                offload("_phase_locking_value", b0, b1)
             for name in measures:
                 if name not in _PAIRWISE:
                     continue
                 src_kind, code, _ = _PAIRWISE[name]
                 src = {"csm": csm, "plv": plv, "pli": pli}[src_kind]
-                dst = out[name][b0:b1]
+                if src_kind == "pli" and not src.is_contiguous():
+                    src = src.contiguous()
+                dst = res[name][b0:b1]
                 with _lib.timed("epilogue"):
                     _lib.check(lib.sc_pairwise_epilogue(code, _lib.ptr(src),
                                                         _lib.ptr(power) if src_kind == "csm" else None, nb, n_freq,
@@ -389,22 +563,25 @@ class Connectivity:
             if want_granger:
                 it_c = torch.zeros((n_pairs, nb), dtype=torch.int32, device=dev)
                 fl_c = torch.zeros((n_pairs, nb), dtype=torch.int32, device=dev)
-                dst = out["pairwise_spectral_granger_prediction"][b0:b1]
+                dst = res["pairwise_spectral_granger_prediction"][b0:b1]
                 with _lib.timed("granger"):
                     rc = lib.sc_granger_pairwise(_lib.ptr(csm), _lib.ptr(power), nb, n_freq, nfft,
                                                  1 if self._hermitian else 0, n_sig, _lib.ptr(pair_t), n_pairs,
                                                  float(tolerance), int(max_iterations), 1 if tail_extrapolation else 0,
                                                  1 if mixed_precision else 0, _lib.ptr(tw128), _lib.ptr(tw64),
                                                  _lib.ptr(dst),
-                                                 _lib.ptr(it_c), _lib.ptr(fl_c), _lib.ptr(gr_ws), ws_bytes, st)
+                                                 _lib.ptr(it_c), _lib.ptr(fl_c), _lib.ptr(exec_cnt), _lib.ptr(gr_ws),
+                                                 ws_bytes, st)
                     _lib.check(rc, "sc_granger_pairwise")
                 it_all[:, b0:b1] = it_c
                 fl_all[:, b0:b1] = fl_c
                 offload("pairwise_spectral_granger_prediction", b0, b1)
+            del item, csm, power, plv, pli
 
         if want_granger:
             self.last_granger_iterations = it_all
             self.last_granger_flags = fl_all
+            self.last_granger_executed = exec_cnt
             n_bad = int((fl_all & _lib.FLAG_NOT_CONVERGED).ne(0).sum())
             n_spd = int((fl_all & _lib.FLAG_NOT_SPD).ne(0).sum())
             if n_bad:  # minimum_phase_decomposition.py:318-322
@@ -421,7 +598,7 @@ class Connectivity:
             for name, t in host.items():
                 result[name] = t.reshape(kept + tuple(t.shape[1:])).numpy()
             return result
-        for name, t in out.items():
+        for name, t in res.items():
             if t.shape[1] != fnn:
                 t = t[:, :fnn]
             tail = tuple(t.shape[1:])
@@ -434,23 +611,14 @@ class Connectivity:
     # ---- reference-named measures -------------------------------------------------------
     def _two_sided(self, name):
         """Expectation over all Nfft bins (the reference's private two-sided quantities)."""
-        lib = _lib.load()
         n_win, n_trials, n_tapers, nfft, n_sig = self._shape
-        kept = self._kept_dims()
+        kept = self._kept_dims(n_local_windows=self._owned(nfft))
         n_batch = int(np.prod(kept)) if kept else 1
-        scale = 1.0 / self.n_observations
         shape = (n_batch, nfft, n_sig) if name == "power" else (n_batch, nfft, n_sig, n_sig)
         dtype = torch.float32 if name == "power" else torch.complex64
         out = torch.empty(shape, dtype=dtype, device=self._device)
-        st = _lib.stream_ptr()
-        for b0, b1, xp, nr in self._chunks(nfft):
-            dst = out[b0:b1]
-            if name == "power":
-                _lib.check(lib.sc_power(_lib.ptr(xp), b1 - b0, nfft, nr, n_sig, scale, _lib.ptr(dst), st), "sc_power")
-            else:
-                _lib.check(lib.sc_csm(_lib.ptr(xp), b1 - b0, nfft, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(dst), st),
-                           "sc_csm")
-            self._allreduce(dst)
+        for item in self._reduced(nfft, [name]):
+            out[item["o0"]:item["o1"]] = item[name]
         return self._finish(out.reshape(kept + tuple(out.shape[1:])))
 
     @property
@@ -570,9 +738,9 @@ class Connectivity:
     def _mvar_bytes(self):
         """Device bytes of the cached path: CSM, G, H, A and the Wilson workspace for every kept index."""
         n_win, n_trials, n_tapers, nfft, n_sig = self._shape
-        kept = self._kept_dims()
-        n_batch = int(np.prod(kept)) if kept else 1
         n_freq = nfft // 2 + 1 if self._hermitian else nfft
+        kept = self._kept_dims(n_local_windows=self._owned(n_freq))
+        n_batch = int(np.prod(kept)) if kept else 1
         return 8 * n_batch * n_freq * n_sig * n_sig * 16
 
     def _mvar_from_csm(self, csm, tolerance, max_iterations):
@@ -632,15 +800,11 @@ class Connectivity:
         lib = _lib.load()
         n_win, n_trials, n_tapers, nfft, n_sig = self._shape
         n_freq = nfft // 2 + 1 if self._hermitian else nfft
-        kept = self._kept_dims()
+        kept = self._kept_dims(n_local_windows=self._owned(n_freq))
         n_batch = int(np.prod(kept)) if kept else 1
-        scale = 1.0 / self.n_observations
-        st = _lib.stream_ptr()
         csm = torch.empty((n_batch, n_freq, n_sig, n_sig), dtype=torch.complex64, device=self._device)
-        for b0, b1, xp, nr in self._chunks(n_freq):
-            _lib.check(lib.sc_csm(_lib.ptr(xp), b1 - b0, n_freq, nr, n_sig, scale, _lib.CSM_CROSS,
-                                  _lib.ptr(csm[b0:b1]), st), "sc_csm")
-            self._allreduce(csm[b0:b1])
+        for item in self._reduced(n_freq, ["csm"]):
+            csm[item["o0"]:item["o1"]] = item["csm"]
         m = self._mvar_from_csm(csm, tolerance, max_iterations)
         self._mvar_warn(m["flags"])
         self.last_wilson_iterations, self.last_wilson_flags = m["iters"], m["flags"]
@@ -667,14 +831,11 @@ class Connectivity:
         # factor + measure per chunk, keep only the result.  The 1e-12-relative Tikhonov terms then use the
         # chunk mean instead of the mean over all windows (a 1e-12-relative change).
         self._mvar_check()
-        lib = _lib.load()
         n_win, n_trials, n_tapers, nfft, n_sig = self._shape
         n_freq = nfft // 2 + 1 if self._hermitian else nfft
         fnn = nfft // 2 + 1
-        kept = self._kept_dims()
+        kept = self._kept_dims(n_local_windows=self._owned(n_freq))
         n_batch = int(np.prod(kept)) if kept else 1
-        scale = 1.0 / self.n_observations
-        st = _lib.stream_ptr()
         to_host = self._output != "torch"
         result = (torch.empty((n_batch, fnn, n_sig, n_sig), dtype=torch.float32, pin_memory=True) if to_host else
                   torch.empty((n_batch, fnn, n_sig, n_sig), dtype=torch.float32, device=self._device))
@@ -682,21 +843,28 @@ class Connectivity:
         all_flags = torch.zeros(n_batch, dtype=torch.int32, device=self._device)
         per_item = 8 * n_freq * n_sig * n_sig * 16
         sub = max(1, self._MVAR_CACHE_BYTES // per_item)
-        for b0, b1, xp, nr in self._chunks(n_freq):
-            csm = torch.empty((b1 - b0, n_freq, n_sig, n_sig), dtype=torch.complex64, device=self._device)
-            _lib.check(lib.sc_csm(_lib.ptr(xp), b1 - b0, n_freq, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(csm), st),
-                       "sc_csm")
-            self._allreduce(csm)
-            del xp
+        copy_stream = _lib.side_stream(self._device, "d2h") if to_host else None
+        for item in self._reduced(n_freq, ["csm"]):
+            b0, b1, csm = item["o0"], item["o1"], item["csm"]
             for c0 in range(0, b1 - b0, sub):
                 c1 = min(b1 - b0, c0 + sub)
                 m = self._mvar_from_csm(csm[c0:c1], tolerance, max_iterations)
                 out = self._mvar_measure_of(m, code)
                 all_iters[b0 + c0:b0 + c1] = m["iters"]
                 all_flags[b0 + c0:b0 + c1] = m["flags"]
-                result[b0 + c0:b0 + c1].copy_(out, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+                if to_host:  # device -> host on the copy stream, under the next sub-chunk's factorisation
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    copy_stream.wait_event(ev)
+                    out.record_stream(copy_stream)
+                    with torch.cuda.stream(copy_stream):
+                        result[b0 + c0:b0 + c1].copy_(out, non_blocking=True)
+                else:
+                    result[b0 + c0:b0 + c1].copy_(out, non_blocking=True)
                 del m, out
+            del item, csm
+        if copy_stream is not None:
+            copy_stream.synchronize()
         self._mvar_warn(all_flags)
         self.last_wilson_iterations, self.last_wilson_flags = all_iters, all_flags
         result = result.reshape(kept + (fnn, n_sig, n_sig))
@@ -753,16 +921,16 @@ class Connectivity:
 
     def _trials_tapers_csm(self, n_freq):
         """Expected CSM over trials x tapers per window (what the SVD-based measures are built on; they
-        merge trials and tapers whatever ``expectation_type`` says, connectivity.py:1953-1976)."""
-        lib = _lib.load()
+        merge trials and tapers whatever ``expectation_type`` says, connectivity.py:1953-1976).  Rows = this rank's
+        windows (all of them unless reduce_scatter)."""
         n_win, n_trials, n_tapers, nfft, n_sig = self._shape
-        scale = 1.0 / (n_trials * n_tapers)
-        csm = torch.empty((n_win, n_freq, n_sig, n_sig), dtype=torch.complex64, device=self._device)
-        st = _lib.stream_ptr()
-        for b0, b1, xp, nr in self._chunks(n_freq, "trials_tapers"):
-            _lib.check(lib.sc_csm(_lib.ptr(xp), b1 - b0, n_freq, nr, n_sig, scale, _lib.CSM_CROSS,
-                                  _lib.ptr(csm[b0:b1]), st), "sc_csm")
-            self._allreduce(csm[b0:b1])
+        gs = self._group_state
+        n_obs = gs.n_trials_tapers if gs is not None else n_trials * n_tapers   # global count under a reduce group
+        n_local = self._owned(n_freq, "trials_tapers")
+        csm = torch.empty((n_win if n_local is None else n_local, n_freq, n_sig, n_sig), dtype=torch.complex64,
+                          device=self._device)
+        for item in self._reduced(n_freq, ["csm"], "trials_tapers", scale=1.0 / n_obs):
+            csm[item["o0"]:item["o1"]] = item["csm"]
         return csm
 
     def canonical_coherence(self, group_labels):
@@ -778,8 +946,10 @@ class Connectivity:
         labels = np.unique(group_labels)
         n_groups = len(labels)
         fnn = nfft // 2 + 1
+        n_loc = self._owned(fnn, "trials_tapers")
+        n_win = n_win if n_loc is None else n_loc       # reduce_scatter: this rank's windows only
         out = torch.full((n_win, fnn, n_groups, n_groups), float("nan"), dtype=torch.float32, device=self._device)
-        if n_groups >= 2:
+        if n_groups >= 2 and n_win > 0:
             order = np.concatenate([np.flatnonzero(group_labels == lab) for lab in labels]).astype(np.int32)
             sizes = np.array([(group_labels == lab).sum() for lab in labels])
             if sizes.max() > 64:
@@ -808,6 +978,7 @@ class Connectivity:
         if n_sig > 1024:
             raise NotImplementedError("global_coherence on the device handles up to 1024 signals")
         csm = self._trials_tapers_csm(nfft)
+        n_win = csm.shape[0]                            # reduce_scatter: this rank's windows only
         val = torch.empty((n_win, nfft, 1), dtype=torch.float32, device=self._device)
         vec = torch.empty((n_win, nfft, n_sig, 1), dtype=torch.complex64, device=self._device)
         n_mat = n_win * nfft
@@ -816,7 +987,7 @@ class Connectivity:
         ws_bytes = lib.sc_global_coherence_workspace_bytes(chunk, n_sig)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=self._device)
         csm_f, val_f, vec_f = csm.reshape(n_mat, n_sig, n_sig), val.reshape(n_mat), vec.reshape(n_mat, n_sig)
-        for m0 in range(0, n_mat, chunk):
+        for m0 in range(0, n_mat, max(chunk, 1)):
             m1 = min(n_mat, m0 + chunk)
             _lib.check(lib.sc_global_coherence(_lib.ptr(csm_f[m0:m1]), m1 - m0, n_sig, _lib.ptr(val_f[m0:m1]),
                                                _lib.ptr(vec_f[m0:m1]), _lib.ptr(ws) if ws_bytes else None, ws_bytes,
@@ -848,24 +1019,27 @@ class Connectivity:
         if keep.size < 2:
             raise IndexError("phase_slope_index needs at least two frequencies in the band of interest")
         fidx = torch.from_numpy(keep.astype(np.int32)).to(self._device)
-        kept = self._kept_dims()
+        kept = self._kept_dims(n_local_windows=self._owned(fnn))
         n_batch = int(np.prod(kept)) if kept else 1
-        scale = 1.0 / self.n_observations
         out = torch.empty((n_batch, n_sig, n_sig), dtype=torch.float32, device=self._device)
         st = _lib.stream_ptr()
-        for b0, b1, xp, nr in self._chunks(fnn):
+        for item in self._reduced(fnn, ["csm", "power"]):
+            b0, b1, csm, power = item["o0"], item["o1"], item["csm"], item["power"]
             nb = b1 - b0
-            power = torch.empty((nb, fnn, n_sig), dtype=torch.float32, device=self._device)
-            csm = torch.empty((nb, fnn, n_sig, n_sig), dtype=torch.complex64, device=self._device)
-            _lib.check(lib.sc_csm(_lib.ptr(xp), nb, fnn, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(csm), st), "sc_csm")
-            self._allreduce(csm)
-            del xp
-            _lib.check(lib.sc_power_from_csm(_lib.ptr(csm), nb * fnn, n_sig, _lib.ptr(power), st), "sc_power_from_csm")
+            if nb == 0:
+                continue
             _lib.check(lib.sc_pairwise_epilogue(_lib.M_COHERENCY, _lib.ptr(csm), _lib.ptr(power), nb, fnn, n_sig,
                                                 float(self.n_observations), _lib.ptr(csm), st), "sc_pairwise_epilogue")
             _lib.check(lib.sc_phase_slope_index(_lib.ptr(csm), nb, fnn, n_sig, _lib.ptr(fidx), int(keep.size),
                                                 _lib.ptr(out[b0:b1]), st), "sc_phase_slope_index")
         return self._finish(out.reshape(kept + (n_sig, n_sig)))
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """Page-locked host array (NumPy view of a pinned torch tensor) for ``Connectivity.compute(out=...)``: reuse it
+    across calls so that a pipeline does not allocate and page-lock its result buffers per call."""
+    t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+    return t.numpy()
 
 
 def all_pairs(n_signals):

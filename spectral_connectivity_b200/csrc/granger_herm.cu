@@ -387,6 +387,9 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
     __syncthreads();
     const long long npairs = p.n_pairs;
     const long long nprob = p.B * npairs;
+    // executed-work counters of this CTA (uniform over the CTA; thread 0 publishes them at the end):
+    // fp32-phase iterations, fp64-phase iterations, closed-form tail steps, problems
+    unsigned long long cnt_f32 = 0, cnt_f64 = 0, cnt_tail = 0, cnt_prob = 0;
     const float fnan = __int_as_float(0x7fc00000);
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
@@ -483,6 +486,7 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                     g10[q] = cmake<double>(f10[q].x * u1, f10[q].y * u1); g11[q] = cmake<double>(f11[q].x * u1, f11[q].y * u1);
                 }
                 it_done = it0;
+                cnt_f32 += it0;
             }
             for (int it = it0; it < p.max_iter && !converged; ++it) {
                 double st[6];
@@ -496,6 +500,7 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                 block_maxn_nonneg<6>(st, redd, phase_d);  // also fences ZA/ZB reuse
                 const double err = sqrt(st[0]);
                 it_done = it + 1;
+                ++cnt_f64;
                 converged = err < p.tol;
                 if (!converged && p.tail && sqrt(st[1]) < kTailRest * p.tol) {
                     // Tail in closed form.  The reference halves every lag-0 coefficient of the causal factor
@@ -542,6 +547,7 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                     }
                     __syncthreads();
                     const double ta = tail_sh[0], tb = tail_sh[1], td = tail_sh[2];
+                    cnt_tail += tail_it[0] - it_done;
                     it_done = tail_it[0];
                     converged = tail_it[1] != 0;
 #pragma unroll
@@ -555,6 +561,7 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
             }
             if (!converged) flag |= SC_FLAG_NOT_CONVERGED;
         }
+        ++cnt_prob;
         if (threadIdx.x == 0) {
             if (p.iters) p.iters[pk * p.B + b] = it_done;
             if (p.flags) p.flags[pk * p.B + b] = flag;
@@ -611,6 +618,12 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                 m[(size_t)cpj * p.S + cpi] = gc10;
             }
         }
+    }
+    if (p.exec_counters && threadIdx.x == 0) {
+        atomicAdd(p.exec_counters + 0, cnt_f32);
+        atomicAdd(p.exec_counters + 1, cnt_f64);
+        atomicAdd(p.exec_counters + 2, cnt_tail);
+        atomicAdd(p.exec_counters + 3, cnt_prob);
     }
 }
 

@@ -298,7 +298,8 @@ extern "C" int sc_granger_pairwise(const void* csm_c64, const float* power, int6
                                    int hermitian_half, int64_t S, const int* pairs, int64_t n_pairs, double tolerance,
                                    int max_iterations, int tail_extrapolation, int mixed_precision,
                                    const void* twiddle_c128, const void* twiddle_c64, float* out_gc, int* out_iters,
-                                   int* out_flags, void* workspace, int64_t workspace_bytes, void* stream) {
+                                   int* out_flags, uint64_t* out_exec_counters, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
     SC_CHECK_ARG(csm_c64 && power && twiddle_c128 && out_gc, "sc_granger_pairwise: null pointer");
     SC_CHECK_ARG(B > 0 && nfft > 0 && S >= 2 && max_iterations >= 0, "sc_granger_pairwise: bad size");
     SC_CHECK_ARG(hermitian_half ? F == nfft / 2 + 1 : F == nfft,
@@ -312,6 +313,7 @@ extern "C" int sc_granger_pairwise(const void* csm_c64, const float* power, int6
     p.tail = tail_extrapolation ? 1 : 0;
     p.mixed = (mixed_precision && twiddle_c64) ? 1 : 0;
     p.tw32 = reinterpret_cast<const cx<float>*>(twiddle_c64);
+    p.exec_counters = reinterpret_cast<unsigned long long*>(out_exec_counters);
     if (hermitian_half && sc_granger_herm_supported(nfft)) return sc_granger_herm_launch(p, stream);
     return w2_launch<1>(p, B * n_pairs, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }

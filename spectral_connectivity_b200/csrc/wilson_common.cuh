@@ -30,6 +30,7 @@ struct W2Params {
     int tail;  // 1: sum the geometric tail of the reference iteration in closed form (Hermitian kernel)
     int mixed; // 1: first iterations in fp32 on the row-scaled problem (Hermitian kernel, needs tw32)
     const cx<float>* tw32;
+    unsigned long long* exec_counters;  // [4] or NULL: fp32 iterations, fp64 iterations, tail steps, problems
     ScFftPlan plan;
 };
 

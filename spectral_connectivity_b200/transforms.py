@@ -287,8 +287,12 @@ class Multitaper:
             self._n_samples_per_time_step = int(self.time_window_step * self.sampling_frequency)
         return self._n_samples_per_time_step
 
+    _n_time_windows_override = None  # distributed.shard_multitaper pins the shard's window count
+
     @property
     def n_time_windows(self):
+        if self._n_time_windows_override is not None:
+            return self._n_time_windows_override
         return sliding_window_count(self.time_series.shape[0], self.n_time_samples_per_window,
                                     self.n_time_samples_per_step)
 

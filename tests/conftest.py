@@ -41,6 +41,10 @@ def assert_parity(got, ref, tol=1e-5, what=""):
     scale = np.nanmax(np.abs(ref))
     scale = scale if scale > 0 else 1.0
     err = np.nanmax(np.abs(got - ref)) / scale
+    log = os.environ.get("SC_PARITY_LOG")   # optional: record the achieved error of every parity check (margins)
+    if log:
+        with open(log, "a") as fh:
+            fh.write(f"{what}\t{err:.3e}\t{tol:.1e}\n")
     assert err <= tol, f"{what}: scale-normalised error {err:.3e} > {tol}"
     ok = np.isclose(got, ref, rtol=tol, atol=tol * scale, equal_nan=True)
     assert ok.all(), f"{what}: {np.count_nonzero(~ok)} elements outside rtol/atol {tol}"

@@ -119,8 +119,62 @@ def config4_section(T, C):
                         granger=gc[0])
 
 
+def round2_section(T, C):
+    """Round-2 fixtures, all from the live reference:
+    * ``cfg3_*``: BASELINE.json configs[2]'s own measures (weighted / plain / debiased phase lag index) on window 0 of
+      its recording, 16 channels (pairwise measures: a channel subset equals that block of the full result; the
+      un-averaged (1,32,7,1000,16,16) CSM is 0.9 GB, all 128 channels would need 59 GB per pass);
+    * ``cfg5_canonical``: configs[4]'s canonical_coherence at ITS grouping (8 groups x 64 channels, 1152
+      observations) on one 60 ms window of the 512-channel recipe of ``series_512``;
+    * canonical coherence with a 70-signal group and with a rank-deficient group (more signals than observations),
+      global coherence with max_rank = 1, 2, 3 (dense-SVD and svds branches);
+    * pairwise Granger and DTF for EVERY expectation type (the reference treats ``csm.shape[0]`` as the unit of
+      convergence whatever that axis is, minimum_phase_decomposition.py:290, 310-315)."""
+    out = {}
+    x3 = series(20261017 + 3, 1_000, 32, 128, 1000.0).astype(np.float32).astype(np.float64)
+    m = T.Multitaper(x3[:, :, :16], sampling_frequency=1000.0, time_halfbandwidth_product=4, time_window_duration=1.0)
+    c = C.Connectivity.from_multitaper(m)
+    for meth in ("weighted_phase_lag_index", "phase_lag_index", "debiased_squared_weighted_phase_lag_index",
+                 "debiased_squared_phase_lag_index"):
+        out[f"cfg3_{meth}"] = np.asarray(getattr(c, meth)())
+    x5 = series_512().astype(np.float64)
+    m = T.Multitaper(x5, sampling_frequency=2000.0, time_halfbandwidth_product=5, time_window_duration=0.060)
+    c = C.Connectivity.from_multitaper(m)
+    cc, lab = c.canonical_coherence(np.arange(512) // 64)
+    out["cfg5_canonical"] = np.asarray(cc)
+    out["cfg5_canonical_labels"] = np.asarray(lab)
+    # groups of 70 + 10 signals, 8 trials x 3 tapers = 24 observations (< 70: rank deficient) and 40 x 3 = 120 (full rank)
+    for tag, n_trials in (("rankdef", 8), ("big", 40)):
+        xg = series(31, 200, n_trials, 80, 100.0)
+        m = T.Multitaper(xg, sampling_frequency=100.0, time_halfbandwidth_product=2, time_window_duration=1.0)
+        c = C.Connectivity.from_multitaper(m)
+        labels = np.where(np.arange(80) < 70, 0, 1)
+        cc, lab = c.canonical_coherence(labels)
+        out[f"canon_{tag}"] = np.asarray(cc)
+    x6 = series(9, 300, 5, 6, 100.0)
+    m6 = T.Multitaper(x6, sampling_frequency=100.0, time_halfbandwidth_product=3, time_window_duration=1.0)
+    c6 = C.Connectivity.from_multitaper(m6)
+    for rank in (1, 2, 3):
+        val, vec = c6.global_coherence(max_rank=rank)
+        out[f"global_rank{rank}_values"] = np.asarray(val)
+        out[f"global_rank{rank}_vectors"] = np.asarray(vec)
+    x4 = series(7, 300, 4, 4, 100.0)
+    m4 = T.Multitaper(x4, sampling_frequency=100.0, time_halfbandwidth_product=3, time_window_duration=1.0)
+    coef = np.asarray(m4.fft())
+    for et in ["trials_tapers", "trials", "tapers", "time", "time_trials", "time_tapers", "time_trials_tapers"]:
+        c = C.Connectivity(coef, expectation_type=et, frequencies=m4.frequencies, time=m4.time)
+        out[f"granger__{et}"] = np.asarray(c.pairwise_spectral_granger_prediction())
+        out[f"dtf__{et}"] = np.asarray(c.directed_transfer_function())
+    np.savez_compressed(os.path.join(HERE, "round2.npz"), **out)
+    for k, v in out.items():
+        print(k, v.shape)
+
+
 def main():
     T, C, M = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        round2_section(T, C)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "config4":
         config4_section(T, C)
         return

@@ -237,7 +237,7 @@ def test_measures_vs_oracle_ragged(sc, n_signals, n_trials):
         return
     got = c.compute(["coherence_magnitude", "weighted_phase_lag_index", "phase_locking_value"])
     assert_parity(got["coherence_magnitude"], O.coherence_magnitude(coef, row_block=16), TOL, "coh")
-    assert_parity(got["weighted_phase_lag_index"], O.weighted_phase_lag_index(coef, row_block=16), 5e-5, "wpli")
+    assert_parity(got["weighted_phase_lag_index"], O.weighted_phase_lag_index(coef, row_block=16), TOL, "wpli")
     assert_parity(got["phase_locking_value"], O.phase_locking_value(coef, row_block=16), TOL, "plv")
 
 
@@ -487,9 +487,10 @@ def test_canonical_coherence_larger_groups_vs_oracle(sc):
     assert np.array_equal(np.isnan(cc), np.isnan(sym)) and np.nanmax(np.abs(cc - sym)) == 0
 
 
-def test_trial_sharded_allreduce_two_gpus(sc):
-    """Partitioning B: ranks hold disjoint trials of the same windows; partial sums are
-    all-reduced over NCCL before the epilogues / Wilson.  Needs two GPUs (skipped otherwise)."""
+def test_trial_sharded_two_gpus(sc):
+    """Partitioning B: ranks hold disjoint (unequal) trial shards of the same windows; partial sums
+    are all-reduced, or reduce-scattered along the window axis so that the epilogues / Wilson run window-sharded.
+    Needs two GPUs (skipped otherwise; `gpurun --gpus 2` log kept under profiles/)."""
     import os
     import subprocess
     import sys
@@ -666,7 +667,7 @@ def test_baseline_config3_windows_vs_live_reference(sc):
     wpli = c.weighted_phase_lag_index()
     coef = O.multitaper_fft(x[:1000].astype(np.float64), 1000.0, O.dpss_tapers(1000, 4, 7, 1000.0), 1000, 1000, 1000)
     # pairwise measure: the first 16 channels' block equals the measure of those 16 channels alone
-    assert_parity(wpli[:1, :, :16, :16], O.weighted_phase_lag_index(coef[..., :16]), 5e-5,
+    assert_parity(wpli[:1, :, :16, :16], O.weighted_phase_lag_index(coef[..., :16]), TOL,
                   "config 3 wPLI (window 0, 16-channel block) vs oracle")
 
 
