@@ -180,7 +180,7 @@ def run_reference(args, wl_name, wl):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pair-freqs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(wl_name, wl, args.gpus, args.scaling, args.shard),
+        "config": workload_config(wl_name, wl, args.gpus, args.scaling, "windows" if args.shard == "auto" else args.shard),
         "cpu_baseline": {"value": value, "unit": "pair-freqs/s", "cores": cpu_threads(), "kind": last["kind"],
                          "sample": last["sample"], "host_cpus": os.cpu_count(),
                          "sample_pair_freqs": last["units"], "measured_seconds_per_step": float(np.mean(secs)),
@@ -364,14 +364,13 @@ def measure_simt_peaks():
     return out
 
 
-def run_gpu(args, wl_name, wl):
+def init_gpu():
+    """Device, CPU affinity and (N > 1) the NCCL process group of this rank -> (rank, world, local, dev, cpus)."""
     import torch
     import torch.distributed as dist
 
-    import spectral_connectivity_b200 as sc
     from spectral_connectivity_b200 import _lib
-    from spectral_connectivity_b200.distributed import bind_to_local_cpus, shard_recording
-
+    from spectral_connectivity_b200.distributed import bind_to_local_cpus
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -385,10 +384,22 @@ def run_gpu(args, wl_name, wl):
             dist.init_process_group("nccl", device_id=dev)
             dist.barrier()
     _lib.load()
+    return rank, world, local, dev, cpus
 
+
+def run_gpu(args, wl_name, wl, shard, ctx):
+    """One measurement (device-resident + end to end) in the given sharding mode; rank 0 returns the JSON line."""
+    import torch
+    import torch.distributed as dist
+
+    import spectral_connectivity_b200 as sc
+    from spectral_connectivity_b200 import _lib
+    from spectral_connectivity_b200.distributed import shard_recording
+
+    rank, world, local, dev, cpus = ctx
     n, n_win, nfft, fnn = geometry(wl)
     strong = world > 1 and args.scaling == "strong"
-    by_trials = strong and args.shard == "trials"
+    by_trials = strong and shard == "trials"
     measures = measures_of(wl_name)
     has_granger = "pairwise_spectral_granger_prediction" in measures
     kw = dict(sampling_frequency=wl["fs"], time_halfbandwidth_product=wl["NW"],
@@ -529,16 +540,33 @@ def run_gpu(args, wl_name, wl):
         barrier()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
         e2e_value = units_total / (e2e_ms * 1e-3)
+    # ---- the host link all ranks share: pinned H2D + D2H copies issued by every rank at the same time ----------
+    def host_link_gbs(nbytes=1 << 28, reps=4):
+        hs, hd = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True), torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        ds, dd = torch.empty(nbytes, dtype=torch.uint8, device=dev), torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        s_in, s_out = _lib.side_stream(dev, "h2d"), _lib.side_stream(dev, "d2h")
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(s_in):
+                dd.copy_(hs, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hd.copy_(ds, non_blocking=True)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        return 2.0 * nbytes * reps * world / dt / 1e9      # aggregate over ranks, both directions
+
+    link_gbs = host_link_gbs()
     h2d_total, d2h_total = int(x_np.nbytes), d2h
     if world > 1:
         t = torch.tensor([h2d_total, d2h_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t)
         h2d_total, d2h_total = int(t[0].item()), int(t[1].item())
 
+    del x_host, x_np, bufs, x_dev
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     # ---- roofline of the dominant kernel + per-stage table (rank 0's kernels) ---------------------------
     peaks = {}
@@ -550,7 +578,7 @@ def run_gpu(args, wl_name, wl):
     tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     simt = measure_simt_peaks()
-    T, S, K = x_dev.shape[1], wl["S"], int(2 * wl["NW"] - 1)
+    T, S, K = (wl["T"] // world if by_trials else wl["T"]), wl["S"], int(2 * wl["NW"] - 1)
     tk = T * K                      # observations this rank contracts over (T/N under trial sharding)
     wloc = n_local_win              # windows this rank transforms
     wown = n_problems // max(S * (S - 1) // 2, 1) if has_granger else (n_win // world if by_trials else n_local_win)
@@ -648,12 +676,18 @@ def run_gpu(args, wl_name, wl):
         "metric": METRIC, "value": value, "unit": "pair-freqs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32 spectra/CSM, f64 Wilson", "data": "synthetic",
-        "config": workload_config(wl_name, wl, world, args.scaling, args.shard),
+        "config": workload_config(wl_name, wl, world, args.scaling, shard),
         "e2e": {"value": e2e_value, "unit": "pair-freqs/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total, "steps": e2e_steps,
                 "warmup": args.e2e_warmup, "ms_each_rank0": [round(v, 1) for v in e2e_each],
                 "host_buffers": "pinned input; results into persistent pinned buffers (compute(out=...))",
                 "cpu_affinity_rank0": cpus,
+                "host_link_gbs_all_ranks": link_gbs,
+                "host_link_floor_ms": ((h2d_total + d2h_total) / (link_gbs * 1e9) * 2 * 1e3 *
+                                       max(h2d_total, d2h_total) / (h2d_total + d2h_total) if link_gbs else None),
+                "host_link_note": "pinned H2D + D2H copies issued by every rank at once (256 MiB x 4 per direction), "
+                                  "aggregate GB/s over both directions; floor = the larger direction's bytes at half "
+                                  "that rate: what the end-to-end step cannot beat on this host whatever the GPUs do",
                 **({} if e2e_ok else {"error": e2e_error or "another rank failed to stage its host buffers"})},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stages": stage_rows, "sanity": sanity,
         "simt_peaks_tflops": simt,
@@ -665,9 +699,7 @@ def run_gpu(args, wl_name, wl):
                                 "host_cpus": os.cpu_count(), "measured_seconds": cb["seconds"],
                                 "sample_pair_freqs": cb["units"],
                                 "est_full_step_seconds": cb["est_full_step_seconds"]}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -678,7 +710,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "replay"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
-    ap.add_argument("--shard", default="windows", choices=["windows", "trials"])
+    ap.add_argument("--shard", default="auto", choices=["auto", "windows", "trials"],
+                    help="N > 1, strong scaling: 'windows' (no collective), 'trials' (reduce_scatter of the partial "
+                         "cross-spectral sums); 'auto' = the headline line is window-sharded and the same run also "
+                         "measures the trial-sharded mode, reported under 'trial_sharded'")
     ap.add_argument("--e2e-warmup", type=int, default=5)
     ap.add_argument("--replay-channels", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -689,7 +724,22 @@ def main():
     elif args.impl == "replay":
         run_replay(args, args.workload, wl)
     else:
-        run_gpu(args, args.workload, wl)
+        import torch.distributed as dist
+        ctx = init_gpu()
+        rank, world = ctx[0], ctx[1]
+        first = "windows" if args.shard == "auto" else args.shard
+        line = run_gpu(args, args.workload, wl, first, ctx)
+        if args.shard == "auto" and world > 1 and args.scaling == "strong" and wl["T"] % world == 0:
+            second = run_gpu(args, args.workload, wl, "trials", ctx)
+            if rank == 0:
+                line["trial_sharded"] = {k: second[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches")}
+                line["trial_sharded"]["parallelism"] = second["config"]["parallelism"]
+                line["trial_sharded"]["stages"] = {k: {"ms_per_step": v["ms_per_step"], "frac": v.get("frac")}
+                                                  for k, v in second["stages"].items()}
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

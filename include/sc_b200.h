@@ -235,6 +235,11 @@ int sc_global_coherence(const void* csm_c64, int64_t BF, int S, float* out_value
                         void* workspace, int64_t workspace_bytes, void* stream);
 int64_t sc_global_coherence_workspace_bytes(int64_t BF, int S);
 
+/* global_coherence(max_rank > 1) -- connectivity.py:2245-2279 keeps the max_rank largest singular values: the
+ * deflation C <- C - lambda v v^H (c64 [BF][S][S], in place) removes the eigenpair sc_global_coherence just returned
+ * (value f32 [BF], vector c64 [BF][S]), so that the next call on the same buffer yields the next eigenpair. */
+int sc_hermitian_deflate(void* csm_c64, int64_t BF, int S, const float* value, const void* vector_c64, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

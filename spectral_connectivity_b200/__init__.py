@@ -8,6 +8,7 @@ from .connectivity import Connectivity, pinned_empty  # noqa: F401
 from .minimum_phase_decomposition import minimum_phase_decomposition  # noqa: F401
 from .transforms import Multitaper  # noqa: F401
 from ._dpss import dpss_windows  # noqa: F401
+from .wrapper import multitaper_connectivity  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["Multitaper", "Connectivity", "minimum_phase_decomposition", "dpss_windows", "pinned_empty"]
+__all__ = ["Multitaper", "Connectivity", "minimum_phase_decomposition", "dpss_windows", "pinned_empty", "multitaper_connectivity"]

@@ -45,6 +45,7 @@ SIGNATURES = {
     "sc_canonical_coherence": (c_int, [_P, c_int64, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
     "sc_global_coherence": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int64, _P]),
     "sc_global_coherence_workspace_bytes": (c_int64, [c_int64, c_int]),
+    "sc_hermitian_deflate": (c_int, [_P, c_int64, c_int, _P, _P, _P]),
     "sc_mvar_measure": (c_int, [c_int, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
 }
 

@@ -8,8 +8,9 @@ spectral Granger prediction through Wilson factorisation (:1161-1213, :2282-2340
 
 Differences from the reference that a user can see, all deliberate:
   * the un-averaged (W,T,K,F,S,S) tensor is never materialised, so ``blocks`` is accepted
-    and ignored; ``dtype`` is accepted, the device pipeline computes in fp32 (complex64)
-    for the spectra/CSM and fp64 for Wilson/Granger;
+    and ignored; the device pipeline computes the spectra / CSM in fp32 (complex64) and Wilson / Granger in
+    mixed fp32 / fp64; ``dtype=np.complex128`` keeps every Wilson iteration in fp64 (default ``None`` =
+    the device default; the reference's default is complex128);
   * one streaming pass over window chunks can produce several measures (``compute``);
   * results are float32 (complex64) NumPy arrays, or CUDA tensors with ``output="torch"``.
 """
@@ -74,14 +75,18 @@ class Connectivity:
     Parameters follow the reference (connectivity.py:277-285).  ``fourier_coefficients`` is
     a 5-D complex array (n_time_windows, n_trials, n_tapers, n_fft_samples, n_signals),
     NumPy or torch.  Extra keyword-only options: ``output`` ("numpy" | "torch"),
-    ``max_chunk_bytes`` (planar-coefficient budget per streamed window chunk) and
+    ``max_chunk_bytes`` (planar-coefficient budget per streamed window chunk),
     ``reduce_group`` (a torch.distributed group whose ranks hold disjoint observation
-    shards -- e.g. trials -- of the same windows; partial sums are all-reduced).
+    shards -- e.g. trials -- of the same windows) with ``reduce_mode`` ("all_reduce": every rank ends with every
+    window; "reduce_scatter": partial sums are summed along the window axis and every rank computes the measures
+    of its own windows, ``owned_windows``), and ``share_csm`` (cache the expected cross-spectral matrix across
+    measures).
     """
 
     def __init__(self, fourier_coefficients, expectation_type="trials_tapers", frequencies=None,
-                 time=None, blocks=None, dtype=np.complex128, *, output="numpy",
-                 max_chunk_bytes=4 << 30, reduce_group=None, reduce_mode="all_reduce", _multitaper=None):
+                 time=None, blocks=None, dtype=None, *, output="numpy",
+                 max_chunk_bytes=4 << 30, reduce_group=None, reduce_mode="all_reduce", share_csm=False,
+                 _multitaper=None):
         src = getattr(fourier_coefficients, "_sc_source", None)
         if (_multitaper is None and src is not None and isinstance(fourier_coefficients, torch.Tensor)
                 and fourier_coefficients._version == src[1]):
@@ -128,11 +133,24 @@ class Connectivity:
         self.expectation_type = expectation_type
         self._frequencies = frequencies
         self._blocks = blocks
+        # ``dtype`` (connectivity.py:277-285 lets the caller pick the cross-spectral precision): None (default) and
+        # complex64 = the device default, float32 spectra / CSM with the mixed-precision Wilson factorisation;
+        # complex128 = keep every Wilson / Granger iteration in float64 (mixed_precision=False becomes the default of
+        # the Granger methods).  Spectra and the CSM stay float32 either way (the tensor-core contraction).
+        if dtype is not None and np.dtype(dtype) not in (np.dtype(np.complex64), np.dtype(np.complex128)):
+            raise ValueError(f"dtype must be complex64 or complex128, got {dtype}")
         self._dtype = dtype
+        self._fp64_wilson = dtype is not None and np.dtype(dtype) == np.dtype(np.complex128)
         self._output = output
         self._max_chunk_bytes = int(max_chunk_bytes)
         self._reduce_group = reduce_group
         self._reduce_mode = reduce_mode
+        # share_csm: keep the expected cross-spectral matrix of the first measure that needs it (if it fits in
+        # _CSM_CACHE_BYTES) so that later measures -- the MVAR family, canonical / global coherence, the phase slope
+        # index, further compute() calls -- skip the FFT + CSM pass (the reference recomputes both per measure,
+        # wrapper.py:265-287)
+        self._share_csm = bool(share_csm)
+        self._csm_cache = {}
         self.time = time if not isinstance(time, torch.Tensor) else time.cpu().numpy()
         self.owned_windows = None  # reduce_scatter mode: global indices of the windows this rank's results hold
         self._group_state = None
@@ -179,7 +197,7 @@ class Connectivity:
 
     @classmethod
     def from_multitaper(cls, multitaper_instance, expectation_type="trials_tapers", blocks=None,
-                        dtype=np.complex128, **kwargs):
+                        dtype=None, **kwargs):
         """Fused path (connectivity.py:366-400): the coefficients are produced window chunk by
         window chunk straight into the layout the CSM kernels read; ``m.fft()`` is not
         materialised."""
@@ -243,7 +261,9 @@ class Connectivity:
         gs = self._group_state
         if gs is None or gs.world == 1:
             per_window = n_trials * n_tapers * n_freq * n_sig * 8
-            return plan_window_chunks(n_win, per_window, self._max_chunk_bytes, shrink_tail=self._output == "numpy")
+            streaming_in = self._mt is not None and bool(getattr(self._mt, "_h2d_events", None))
+            return plan_window_chunks(n_win, per_window, self._max_chunk_bytes, shrink_tail=self._output == "numpy",
+                                      grow_head=streaming_in)
         # reduce group: every rank must derive the same bounds -> only group-agreed numbers; the chunk is also the
         # granularity of the collective, so the reduced sums (CSM: S^2 * 8 bytes per window and bin) count too.
         # Sized for all nfft bins whatever ``n_freq`` is streamed, so that the window ownership under
@@ -306,6 +326,20 @@ class Connectivity:
         comm = _lib.side_stream(dev, "comm") if reduce else None
         st = _lib.stream_ptr()
         kinds = set(kinds)
+        cached = self._csm_cache.get((n_freq, et)) if kinds <= {"csm", "power"} and "csm" in kinds else None
+        if cached is not None:      # share_csm: an earlier measure already produced these sums
+            rows_per_item = max(1, (1 << 30) // max(n_freq * n_sig * n_sig * 8, 1))
+            for o0 in range(0, cached.shape[0], rows_per_item):
+                o1 = min(cached.shape[0], o0 + rows_per_item)
+                item = dict(o0=o0, o1=o1, w0=o0, w1=o1, csm=cached[o0:o1])
+                if "power" in kinds:
+                    power = torch.empty((o1 - o0, n_freq, n_sig), dtype=torch.float32, device=dev)
+                    with _lib.timed("power"):
+                        _lib.check(lib.sc_power_from_csm(_lib.ptr(item["csm"]), (o1 - o0) * n_freq, n_sig,
+                                                         _lib.ptr(power), st), "sc_power_from_csm")
+                    item["power"] = power
+                yield item
+            return
         want_power = "power" in kinds
         sums = [k for k in ("csm", "plv", "pli") if k in kinds]
         if want_power and "csm" not in kinds:
@@ -373,7 +407,11 @@ class Connectivity:
                             dist.reduce_scatter_tensor(r[a], t[a], op=dist.ReduceOp.SUM, group=self._reduce_group)
                     else:
                         r = torch.empty((own,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-                        dist.reduce_scatter_tensor(r, t, op=dist.ReduceOp.SUM, group=self._reduce_group)
+                        if t.is_complex():   # NCCL has no complex types: sum the interleaved (re, im) floats
+                            dist.reduce_scatter_tensor(torch.view_as_real(r), torch.view_as_real(t),
+                                                       op=dist.ReduceOp.SUM, group=self._reduce_group)
+                        else:
+                            dist.reduce_scatter_tensor(r, t, op=dist.ReduceOp.SUM, group=self._reduce_group)
                     item[kind + "_partial"] = t      # keep the send buffer alive until the consumer has run
                     item[kind] = r
                 done = torch.cuda.Event()
@@ -421,8 +459,34 @@ class Connectivity:
         if pending is not None:
             yield finish(pending)
 
+    _CSM_CACHE_BYTES = 24 << 30
+
+    def _local_csm(self, n_freq, expectation_type=None, scale=None, private=False):
+        """The expected cross-spectral matrix of every window this rank holds, c64 [rows][n_freq][S][S]; cached on the
+        object with ``share_csm`` (``private=True`` returns a buffer the caller may overwrite)."""
+        et = expectation_type or self.expectation_type
+        n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        key = (n_freq, et)
+        hit = self._csm_cache.get(key)
+        if hit is None and self._hermitian and n_freq == nfft and (nfft // 2 + 1, et) in self._csm_cache:
+            half = self._csm_cache[(nfft // 2 + 1, et)]      # real series: C(-f) = conj C(f)
+            mirror = half[:, 1:nfft - nfft // 2].flip(1).conj()
+            return torch.cat([half, mirror], dim=1)
+        if hit is not None:
+            return hit.clone() if private else hit
+        n_local = self._owned(n_freq, et)
+        kept = self._kept_dims(et, n_local_windows=n_local)
+        rows = int(np.prod(kept)) if kept else 1
+        csm = torch.empty((rows, n_freq, n_sig, n_sig), dtype=torch.complex64, device=self._device)
+        for item in self._reduced(n_freq, ["csm"], et, scale=scale):
+            csm[item["o0"]:item["o1"]] = item["csm"]
+        if self._share_csm and csm.numel() * 8 <= self._CSM_CACHE_BYTES:
+            self._csm_cache[key] = csm
+            return csm.clone() if private else csm
+        return csm
+
     def compute(self, measures, pairs=None, tolerance=1e-8, max_iterations=60, tail_extrapolation=True,
-                mixed_precision=True, out=None):
+                mixed_precision=None, out=None):
         """Compute several measures in ONE streaming pass over window chunks.
 
         ``measures``: iterable of names from ``MEASURES``.  Returns {name: array}.  Per chunk
@@ -443,6 +507,8 @@ class Connectivity:
         With ``reduce_mode="reduce_scatter"`` the results hold this rank's windows only (``owned_windows``)."""
         lib = _lib.load()
         measures = list(measures)
+        if mixed_precision is None:
+            mixed_precision = not self._fp64_wilson
         for name in measures:
             if name not in MEASURES:
                 raise ValueError(f"unknown measure '{name}'")
@@ -700,7 +766,7 @@ class Connectivity:
         return self._one("pairwise_phase_consistency")
 
     def pairwise_spectral_granger_prediction(self, tolerance=1e-8, max_iterations=60, tail_extrapolation=True,
-                                             mixed_precision=True):
+                                             mixed_precision=None):
         """Spectral Granger prediction for every signal pair; [..., i, j] is the influence
         j -> i (connectivity.py:1161-1191)."""
         return self._one("pairwise_spectral_granger_prediction", tolerance=tolerance,
@@ -708,7 +774,7 @@ class Connectivity:
                          mixed_precision=mixed_precision)
 
     def subset_pairwise_spectral_granger_prediction(self, pairs, tolerance=1e-8, max_iterations=60,
-                                                    tail_extrapolation=True, mixed_precision=True):
+                                                    tail_extrapolation=True, mixed_precision=None):
         """connectivity.py:1193-1213."""
         return self._one("pairwise_spectral_granger_prediction", pairs=pairs, tolerance=tolerance,
                          max_iterations=max_iterations, tail_extrapolation=tail_extrapolation,
@@ -802,9 +868,7 @@ class Connectivity:
         n_freq = nfft // 2 + 1 if self._hermitian else nfft
         kept = self._kept_dims(n_local_windows=self._owned(n_freq))
         n_batch = int(np.prod(kept)) if kept else 1
-        csm = torch.empty((n_batch, n_freq, n_sig, n_sig), dtype=torch.complex64, device=self._device)
-        for item in self._reduced(n_freq, ["csm"]):
-            csm[item["o0"]:item["o1"]] = item["csm"]
+        csm = self._local_csm(n_freq)
         m = self._mvar_from_csm(csm, tolerance, max_iterations)
         self._mvar_warn(m["flags"])
         self.last_wilson_iterations, self.last_wilson_flags = m["iters"], m["flags"]
@@ -919,25 +983,28 @@ class Connectivity:
         raise NotImplementedError(
             f"{name} is outside the current hot-path scope (SURVEY.md section 8f); see DESIGN.md")
 
-    def _trials_tapers_csm(self, n_freq):
+    def _trials_tapers_csm(self, n_freq, private=False):
         """Expected CSM over trials x tapers per window (what the SVD-based measures are built on; they
         merge trials and tapers whatever ``expectation_type`` says, connectivity.py:1953-1976).  Rows = this rank's
         windows (all of them unless reduce_scatter)."""
         n_win, n_trials, n_tapers, nfft, n_sig = self._shape
         gs = self._group_state
         n_obs = gs.n_trials_tapers if gs is not None else n_trials * n_tapers   # global count under a reduce group
-        n_local = self._owned(n_freq, "trials_tapers")
-        csm = torch.empty((n_win if n_local is None else n_local, n_freq, n_sig, n_sig), dtype=torch.complex64,
-                          device=self._device)
-        for item in self._reduced(n_freq, ["csm"], "trials_tapers", scale=1.0 / n_obs):
-            csm[item["o0"]:item["o1"]] = item["csm"]
-        return csm
+        return self._local_csm(n_freq, "trials_tapers", scale=1.0 / n_obs, private=private)
 
     def canonical_coherence(self, group_labels):
         """Squared canonical coherence between signal groups, shape (n_windows, n_frequencies, n_groups,
         n_groups) with NaN diagonal, and the sorted group labels (connectivity.py:745-820).  Computed from
-        the expected CSM (block whitening) instead of per-group SVDs of the coefficients; groups of up to
-        64 signals, each needing at least as many observations (trials x tapers) as signals."""
+        the expected CSM (block whitening C_aa^-1/2 C_ab C_bb^-1/2) instead of per-group SVDs of the coefficients.
+
+        * groups of up to 64 signals: one fused kernel (two Cholesky factorisations, two triangular solves and the
+          top eigenvalue per (window, frequency, group pair) in shared memory) -- BASELINE config 5's grouping;
+        * a group with at least as many signals as observations (trials x tapers) spans the whole observation space:
+          the reference's SVD whitening U V^H then has V unitary, every singular value of the whitened cross product
+          is exactly 1, and so is the result for every pair that involves such a group (connectivity.py:1997-2000,
+          2027-2031) -- returned directly;
+        * larger full-rank groups: same block whitening through batched cuSOLVER calls (torch.linalg, complex128),
+          a library path kept for completeness."""
         lib = _lib.load()
         group_labels = np.asarray(group_labels)
         n_win, n_trials, n_tapers, nfft, n_sig = self._shape
@@ -950,49 +1017,108 @@ class Connectivity:
         n_win = n_win if n_loc is None else n_loc       # reduce_scatter: this rank's windows only
         out = torch.full((n_win, fnn, n_groups, n_groups), float("nan"), dtype=torch.float32, device=self._device)
         if n_groups >= 2 and n_win > 0:
-            order = np.concatenate([np.flatnonzero(group_labels == lab) for lab in labels]).astype(np.int32)
-            sizes = np.array([(group_labels == lab).sum() for lab in labels])
-            if sizes.max() > 64:
-                raise NotImplementedError("canonical_coherence on the device handles groups of up to 64 signals")
-            offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
-            gidx = torch.from_numpy(order).to(self._device)
-            goff = torch.from_numpy(offsets).to(self._device)
-            csm = self._trials_tapers_csm(fnn)
-            flags = torch.zeros(n_win * fnn, dtype=torch.int32, device=self._device)
-            _lib.check(lib.sc_canonical_coherence(_lib.ptr(csm), n_win, fnn, n_sig, _lib.ptr(gidx), _lib.ptr(goff),
-                                                  n_groups, int(sizes.max()), _lib.ptr(out), _lib.ptr(flags),
-                                                  _lib.stream_ptr()), "sc_canonical_coherence")
-            if int(flags.ne(0).sum()):
-                logger.warning("canonical_coherence: some group blocks of the cross-spectral matrix are not positive "
-                               "definite (fewer observations than signals in a group); those entries are NaN.")
+            members = [np.flatnonzero(group_labels == lab) for lab in labels]
+            sizes = np.array([len(m) for m in members])
+            gs = self._group_state
+            n_obs = gs.n_trials_tapers if gs is not None else n_trials * n_tapers
+            saturated = sizes >= n_obs                  # rank-deficient groups: canonical coherence is exactly 1
+            regular = np.flatnonzero(~saturated)
+            if len(regular) >= 2:
+                csm = self._trials_tapers_csm(fnn)
+                sub = torch.full((n_win, fnn, len(regular), len(regular)), float("nan"), dtype=torch.float32,
+                                 device=self._device)
+                if sizes[regular].max() <= 64:
+                    order = np.concatenate([members[g] for g in regular]).astype(np.int32)
+                    offsets = np.concatenate([[0], np.cumsum(sizes[regular])]).astype(np.int32)
+                    gidx = torch.from_numpy(order).to(self._device)
+                    goff = torch.from_numpy(offsets).to(self._device)
+                    flags = torch.zeros(n_win * fnn, dtype=torch.int32, device=self._device)
+                    _lib.check(lib.sc_canonical_coherence(_lib.ptr(csm), n_win, fnn, n_sig, _lib.ptr(gidx), _lib.ptr(goff),
+                                                          len(regular), int(sizes[regular].max()), _lib.ptr(sub),
+                                                          _lib.ptr(flags), _lib.stream_ptr()), "sc_canonical_coherence")
+                    bad = int(flags.ne(0).sum())
+                else:
+                    bad = self._canonical_large_groups(csm, [members[g] for g in regular], sub)
+                if bad:
+                    logger.warning("canonical_coherence: some group blocks of the cross-spectral matrix are not positive "
+                                   "definite (linearly dependent signals in a group); those entries are NaN.")
+                ridx = torch.from_numpy(regular).to(self._device)
+                out[:, :, ridx[:, None], ridx[None, :]] = sub
+            for g in np.flatnonzero(saturated):
+                out[:, :, g, :] = 1.0
+                out[:, :, :, g] = 1.0
+            diag = torch.arange(n_groups, device=self._device)
+            out[:, :, diag, diag] = float("nan")
         return self._finish(out), labels
 
+    def _canonical_large_groups(self, csm, members, out):
+        """Block whitening for groups of more than 64 signals (batched cuSOLVER through torch.linalg, complex128):
+        sigma_max^2(L_a^-1 C_ab L_b^-H) with C_gg = L_g L_g^H.  Returns the number of non-positive-definite blocks."""
+        dev = self._device
+        idx = [torch.from_numpy(np.asarray(m)).to(dev) for m in members]
+        n_bad = 0
+        per_window = csm.shape[1] * max(len(m) for m in members) ** 2 * 16 * 6
+        step = max(1, (2 << 30) // max(per_window, 1))
+        for w0 in range(0, csm.shape[0], step):
+            c = csm[w0:w0 + step].to(torch.complex128)
+            chol = []
+            for ia in idx:
+                fac, info = torch.linalg.cholesky_ex(c[:, :, ia[:, None], ia[None, :]])
+                n_bad += int(info.ne(0).sum())
+                chol.append((fac, info.ne(0)))
+            for a in range(len(idx)):
+                for b in range(a + 1, len(idx)):
+                    cab = c[:, :, idx[a][:, None], idx[b][None, :]]
+                    m = torch.linalg.solve_triangular(chol[a][0], cab, upper=False)
+                    m = torch.linalg.solve_triangular(chol[b][0], m.mH, upper=False)
+                    val = torch.linalg.matrix_norm(m, ord=2) ** 2
+                    val = torch.where(chol[a][1] | chol[b][1], torch.full_like(val, float("nan")), val)
+                    out[w0:w0 + step, :, a, b] = out[w0:w0 + step, :, b, a] = val.to(torch.float32)
+        return n_bad
+
     def global_coherence(self, max_rank=1):
-        """Largest eigenvalue of the cross-spectral matrix per (window, frequency) over ALL n_fft bins and
-        its eigenvector: shapes (n_windows, n_fft, 1) and (n_windows, n_fft, n_signals, 1)
-        (connectivity.py:822-895).  The eigenvector is defined up to a phase, as in the reference's SVD."""
-        if max_rank != 1:
-            raise NotImplementedError("global_coherence on the device returns the leading component only (max_rank=1)")
+        """The ``max_rank`` largest eigenvalues of the cross-spectral matrix per (window, frequency) over ALL n_fft
+        bins and their eigenvectors: shapes (n_windows, n_fft, max_rank) and (n_windows, n_fft, n_signals, max_rank)
+        (connectivity.py:822-895, 2245-2279).  Eigenvectors are defined up to a phase, as in the reference's SVD.
+        Eigenpairs are found one at a time (repeated squaring, then deflation C <- C - lambda v v^H); the ORDER
+        along the last axis is the reference's: descending from its dense SVD when max_rank >= n_signals - 1,
+        ascending from scipy's ``svds`` otherwise (:2258-2276)."""
         lib = _lib.load()
         n_win, n_trials, n_tapers, nfft, n_sig = self._shape
+        max_rank = int(max_rank)
+        if max_rank < 1:
+            raise ValueError("max_rank must be at least 1")
         if n_sig > 1024:
             raise NotImplementedError("global_coherence on the device handles up to 1024 signals")
-        csm = self._trials_tapers_csm(nfft)
+        gs = self._group_state
+        n_obs = gs.n_trials_tapers if gs is not None else n_trials * n_tapers
+        n_keep = min(max_rank, n_sig, n_obs)            # the SVD of an (S x TK) matrix has min(S, TK) singular values
+        csm = self._trials_tapers_csm(nfft, private=max_rank > 1)   # deflation overwrites its buffer
         n_win = csm.shape[0]                            # reduce_scatter: this rank's windows only
-        val = torch.empty((n_win, nfft, 1), dtype=torch.float32, device=self._device)
-        vec = torch.empty((n_win, nfft, n_sig, 1), dtype=torch.complex64, device=self._device)
+        val = torch.empty((n_keep, n_win, nfft), dtype=torch.float32, device=self._device)
+        vec = torch.empty((n_keep, n_win, nfft, n_sig), dtype=torch.complex64, device=self._device)
         n_mat = n_win * nfft
         per = max(1, lib.sc_global_coherence_workspace_bytes(1, n_sig))
         chunk = n_mat if n_sig <= 64 else max(1, min(n_mat, (8 << 30) // per))  # <= 8 GiB of squaring workspace
         ws_bytes = lib.sc_global_coherence_workspace_bytes(chunk, n_sig)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=self._device)
-        csm_f, val_f, vec_f = csm.reshape(n_mat, n_sig, n_sig), val.reshape(n_mat), vec.reshape(n_mat, n_sig)
-        for m0 in range(0, n_mat, max(chunk, 1)):
-            m1 = min(n_mat, m0 + chunk)
-            _lib.check(lib.sc_global_coherence(_lib.ptr(csm_f[m0:m1]), m1 - m0, n_sig, _lib.ptr(val_f[m0:m1]),
-                                               _lib.ptr(vec_f[m0:m1]), _lib.ptr(ws) if ws_bytes else None, ws_bytes,
-                                               _lib.stream_ptr()), "sc_global_coherence")
-        return self._finish(val), self._finish(vec)
+        csm_f = csm.reshape(n_mat, n_sig, n_sig)
+        st = _lib.stream_ptr()
+        for r in range(n_keep):
+            val_f, vec_f = val[r].reshape(n_mat), vec[r].reshape(n_mat, n_sig)
+            for m0 in range(0, n_mat, max(chunk, 1)):
+                m1 = min(n_mat, m0 + chunk)
+                _lib.check(lib.sc_global_coherence(_lib.ptr(csm_f[m0:m1]), m1 - m0, n_sig, _lib.ptr(val_f[m0:m1]),
+                                                   _lib.ptr(vec_f[m0:m1]), _lib.ptr(ws) if ws_bytes else None, ws_bytes,
+                                                   st), "sc_global_coherence")
+            if r + 1 < n_keep and n_mat:
+                _lib.check(lib.sc_hermitian_deflate(_lib.ptr(csm_f), n_mat, n_sig, _lib.ptr(val_f), _lib.ptr(vec_f), st),
+                           "sc_hermitian_deflate")
+        val = val.permute(1, 2, 0)                      # (W, nfft, rank), descending
+        vec = vec.permute(1, 2, 3, 0)                   # (W, nfft, S, rank)
+        if max_rank < n_sig - 1:                        # the reference's svds branch returns ascending order
+            val, vec = val.flip(-1), vec.flip(-1)
+        return self._finish(val.contiguous()), self._finish(vec.contiguous())
 
     def group_delay(self, *args, **kwargs):
         self._next_round("group_delay")
@@ -1028,9 +1154,10 @@ class Connectivity:
             nb = b1 - b0
             if nb == 0:
                 continue
+            coh = torch.empty_like(csm)      # not in place: the CSM may be the shared cache
             _lib.check(lib.sc_pairwise_epilogue(_lib.M_COHERENCY, _lib.ptr(csm), _lib.ptr(power), nb, fnn, n_sig,
-                                                float(self.n_observations), _lib.ptr(csm), st), "sc_pairwise_epilogue")
-            _lib.check(lib.sc_phase_slope_index(_lib.ptr(csm), nb, fnn, n_sig, _lib.ptr(fidx), int(keep.size),
+                                                float(self.n_observations), _lib.ptr(coh), st), "sc_pairwise_epilogue")
+            _lib.check(lib.sc_phase_slope_index(_lib.ptr(coh), nb, fnn, n_sig, _lib.ptr(fidx), int(keep.size),
                                                 _lib.ptr(out[b0:b1]), st), "sc_phase_slope_index")
         return self._finish(out.reshape(kept + (n_sig, n_sig)))
 

@@ -101,10 +101,13 @@ template <> struct RealOps<float> {
 __device__ __forceinline__ float log_ratio(double total, double part) {
     double rest = total - part;
     if (rest == 0.0) rest = kEps64;
-    const double ratio = rest / total;
+    // the differences are formed in fp64; the quotients are taken in fp32 (the output is float32 and a
+    // correctly rounded fp32 division of two fp32-rounded operands is accurate to 2e-7 relative)
+    const float ftotal = (float)total;
+    const float ratio = (float)rest / ftotal;
     float gc;
-    if (ratio >= 0.5) gc = -log1pf((float)((rest - total) / total));  // = -log1p(-(total - rest)/total)
-    else gc = -logf((float)ratio);
+    if (ratio >= 0.5f) gc = -log1pf((float)(rest - total) / ftotal);  // = -log1p(-(total - rest)/total)
+    else gc = -logf(ratio);
     return gc > 0.f ? gc : __int_as_float(0x7fc00000);
 }
 
@@ -260,39 +263,54 @@ struct PlusWindowDefect {
     }
 };
 
-// Defect-correction form of one fp64 Wilson iteration (mixed-precision mode).  Near the fixed point
+// Defect-correction form of one fp64-phase Wilson iteration (mixed-precision mode).  Near the fixed point
 // B = G^-1 S G^-H + I = 2I + E with a small E, and the plus operator is linear with [2I]+ = I, so
-// G P = G + G [E]+.  E is formed per bin in fp64 (the cancellation M - I happens there), but its causal
-// projection -- the four FFTs, i.e. nearly all of the shared-memory traffic -- runs in FP32: an FFT error
-// of 1e-7 RELATIVE TO E (|E| <~ 1e-3 when fp64 takes over, 1e-6 at the last iteration) moves G by ~1e-10
-// absolute, two orders below the 1e-8 stopping tolerance and far below the float32 output.  Same outputs as
-// herm_iteration<double> (stat[], lag0[] as float).
+// G P = G + G [E]+.  The defect is E = G^-1 (S - G G^H) G^-H: ONLY the residual R = S - G G^H suffers
+// cancellation, so it alone is formed in fp64 (about 40 flops per bin); everything downstream of it -- the two
+// congruence products with G^-1, the causal projection (four FFTs) and the product G [E]+ -- is LINEAR in R and
+// runs in FP32 on the row-scaled problem (G' = D G, R' = D R D with D = diag(r0, r1), which leaves E unchanged
+// and keeps every intermediate O(|E|) or O(1)): an fp32 error of ~3e-7 RELATIVE TO E (|E| <~ 1e-3 when fp64
+// takes over, 1e-6 at the last iteration) moves G by ~1e-11 absolute, three orders below the 1e-8 stopping
+// tolerance.  G itself is accumulated in fp64 (G += D^-1 dG').  Same outputs as herm_iteration<double>
+// (stat[], lag0[] as float); the maxima are taken per row in scaled units and unscaled once per thread.
 template <int FPT, typename FFT>
 __device__ __forceinline__ void herm_iteration_defect(cd (&g00)[FPT], cd (&g01)[FPT], cd (&g10)[FPT], cd (&g11)[FPT],
                                                       const float (&s00)[FPT], const float (&s11)[FPT],
-                                                      const float2 (&s01)[FPT], cx<float>* ZA, cx<float>* ZB,
-                                                      const ScFftPlan& plan, const cx<float>* tw, int N, int fnn,
-                                                      float* lag0, double (&stat)[6]) {
+                                                      const float2 (&s01)[FPT], float r0, float r1, cx<float>* ZA,
+                                                      cx<float>* ZB, const ScFftPlan& plan, const cx<float>* tw, int N,
+                                                      int fnn, float* lag0, double (&stat)[6]) {
+    const double dr0 = (double)r0, dr1 = (double)r1;
+    const double k00 = dr0 * dr0, k11 = dr1 * dr1, k01 = dr0 * dr1;
 #pragma unroll
     for (int q = 0; q < FPT; ++q) {
         const int f = threadIdx.x + q * kThreads;
         if (f < fnn) {
-            const cd det = csub(cmul(g00[q], g11[q]), cmul(g01[q], g10[q]));
-            const double dn = 1.0 / (det.x * det.x + det.y * det.y);
-            const cd idet = cmake<double>(det.x * dn, -det.y * dn);
-            const cd u0 = cmul(g11[q], idet), u1 = cmul(g01[q], idet);
-            const cd v0 = cmul(g10[q], idet), v1 = cmul(g00[q], idet);
-            const double a = (double)s00[q], d = (double)s11[q];
-            const cd c = cmake<double>((double)s01[q].x, (double)s01[q].y);
-            const cd cc = cconj(c);
-            const cd t00 = csub(cscale(u0, a), cmul(u1, cc));
-            const cd t01 = csub(cmul(u0, c), cscale(u1, d));
-            const cd t10 = csub(cmul(v1, cc), cscale(v0, a));
-            const cd t11 = csub(cscale(v1, d), cmul(v0, c));
-            const float e00 = (float)((t00.x * u0.x + t00.y * u0.y) - (t01.x * u1.x + t01.y * u1.y) - 1.0);
-            const float e11 = (float)((t11.x * v1.x + t11.y * v1.y) - (t10.x * v0.x + t10.y * v0.y) - 1.0);
-            const float e01x = (float)(-(t00.x * v0.x + t00.y * v0.y) + (t01.x * v1.x + t01.y * v1.y));
-            const float e01y = (float)(-(t00.y * v0.x - t00.x * v0.y) + (t01.y * v1.x - t01.x * v1.y));
+            // residual R = S - G G^H in fp64, scaled: R' = D R D
+            const double n00 = g00[q].x * g00[q].x + g00[q].y * g00[q].y + g01[q].x * g01[q].x + g01[q].y * g01[q].y;
+            const double n11 = g10[q].x * g10[q].x + g10[q].y * g10[q].y + g11[q].x * g11[q].x + g11[q].y * g11[q].y;
+            const double n01x = g00[q].x * g10[q].x + g00[q].y * g10[q].y + g01[q].x * g11[q].x + g01[q].y * g11[q].y;
+            const double n01y = g00[q].y * g10[q].x - g00[q].x * g10[q].y + g01[q].y * g11[q].x - g01[q].x * g11[q].y;
+            const float a = (float)(((double)s00[q] - n00) * k00), d = (float)(((double)s11[q] - n11) * k11);
+            const cx<float> c = cmake<float>((float)(((double)s01[q].x - n01x) * k01), (float)(((double)s01[q].y - n01y) * k01));
+            // scaled factor G' = D G and its inverse in fp32
+            const cx<float> f00 = cmake<float>((float)(g00[q].x * dr0), (float)(g00[q].y * dr0));
+            const cx<float> f01 = cmake<float>((float)(g01[q].x * dr0), (float)(g01[q].y * dr0));
+            const cx<float> f10 = cmake<float>((float)(g10[q].x * dr1), (float)(g10[q].y * dr1));
+            const cx<float> f11 = cmake<float>((float)(g11[q].x * dr1), (float)(g11[q].y * dr1));
+            const cx<float> det = csub(cmul(f00, f11), cmul(f01, f10));
+            const float dn = 1.0f / (det.x * det.x + det.y * det.y);
+            const cx<float> idet = cmake<float>(det.x * dn, -det.y * dn);
+            const cx<float> u0 = cmul(f11, idet), u1 = cmul(f01, idet);   // row 0 of G'^-1 = (u0, -u1)
+            const cx<float> v0 = cmul(f10, idet), v1 = cmul(f00, idet);   // row 1 of G'^-1 = (-v0, v1)
+            const cx<float> cc = cconj(c);
+            const cx<float> t00 = csub(cscale(u0, a), cmul(u1, cc));
+            const cx<float> t01 = csub(cmul(u0, c), cscale(u1, d));
+            const cx<float> t10 = csub(cmul(v1, cc), cscale(v0, a));
+            const cx<float> t11 = csub(cscale(v1, d), cmul(v0, c));
+            const float e00 = (t00.x * u0.x + t00.y * u0.y) - (t01.x * u1.x + t01.y * u1.y);
+            const float e11 = (t11.x * v1.x + t11.y * v1.y) - (t10.x * v0.x + t10.y * v0.y);
+            const float e01x = -(t00.x * v0.x + t00.y * v0.y) + (t01.x * v1.x + t01.y * v1.y);
+            const float e01y = -(t00.y * v0.x - t00.x * v0.y) + (t01.y * v1.x - t01.x * v1.y);
             const int fm = f == 0 ? 0 : N - f;
             ZA[f] = cmake<float>(e00, e11);
             ZA[fm] = cmake<float>(e00, e11);
@@ -325,8 +343,10 @@ __device__ __forceinline__ void herm_iteration_defect(cd (&g00)[FPT], cd (&g01)[
         __syncthreads();
         Q = FFT::template run2<float>(o, c, plan, tw, false);
     }
-    double err2 = 0.0, rest2 = 0.0, c00 = 0.0, c10 = 0.0, c01m = 0.0, c11m = 0.0;
-    const double h00 = 0.5 * (double)lag0[0], h01 = 0.5 * (double)lag0[1], h11 = 0.5 * (double)lag0[2];  // P0 - I
+    // row-wise maxima in scaled units: row 0 scales back by 1/r0, row 1 by 1/r1
+    float err_r0 = 0.f, err_r1 = 0.f, rest_r0 = 0.f, rest_r1 = 0.f, c00 = 0.f, c10 = 0.f, c01m = 0.f, c11m = 0.f;
+    const float h00 = 0.5f * lag0[0], h01 = 0.5f * lag0[1], h11 = 0.5f * lag0[2];  // P0 - I
+    const double i0 = 1.0 / dr0, i1 = 1.0 / dr1;
 #pragma unroll
     for (int q = 0; q < FPT; ++q) {
         const int f = threadIdx.x + q * kThreads;
@@ -334,33 +354,43 @@ __device__ __forceinline__ void herm_iteration_defect(cd (&g00)[FPT], cd (&g01)[
             const int fm = f == 0 ? 0 : N - f;
             const cx<float> a1 = Q[f], m1 = Q[fm], a2 = Q[N + f], m2 = Q[N + fm];
             // [E]+ : Y1 = P00 + i P11, Y2 = P01 + i P10 (spectra of real sequences)
-            const cd p00 = cmake<double>(0.5 * ((double)a1.x + m1.x), 0.5 * ((double)a1.y - m1.y));
-            const cd p11 = cmake<double>(0.5 * ((double)a1.y + m1.y), 0.5 * ((double)m1.x - a1.x));
-            const cd p01 = cmake<double>(0.5 * ((double)a2.x + m2.x), 0.5 * ((double)a2.y - m2.y));
-            const cd p10 = cmake<double>(0.5 * ((double)a2.y + m2.y), 0.5 * ((double)m2.x - a2.x));
-            // dG = G [E]+
-            cd d00 = cadd(cmul(g00[q], p00), cmul(g01[q], p10));
-            cd d01 = cadd(cmul(g00[q], p01), cmul(g01[q], p11));
-            cd d10 = cadd(cmul(g10[q], p00), cmul(g11[q], p10));
-            cd d11 = cadd(cmul(g10[q], p01), cmul(g11[q], p11));
-            err2 = fmax(err2, fmax(fmax(d00.x * d00.x + d00.y * d00.y, d01.x * d01.x + d01.y * d01.y),
-                                   fmax(d10.x * d10.x + d10.y * d10.y, d11.x * d11.x + d11.y * d11.y)));
-            c00 = fmax(c00, g00[q].x * g00[q].x + g00[q].y * g00[q].y);
-            c10 = fmax(c10, g10[q].x * g10[q].x + g10[q].y * g10[q].y);
-            c01m = fmax(c01m, g01[q].x * g01[q].x + g01[q].y * g01[q].y);
-            c11m = fmax(c11m, g11[q].x * g11[q].x + g11[q].y * g11[q].y);
-            const cd n00 = cadd(g00[q], d00), n01 = cadd(g01[q], d01), n10 = cadd(g10[q], d10), n11 = cadd(g11[q], d11);
+            const cx<float> p00 = cmake<float>(0.5f * (a1.x + m1.x), 0.5f * (a1.y - m1.y));
+            const cx<float> p11 = cmake<float>(0.5f * (a1.y + m1.y), 0.5f * (m1.x - a1.x));
+            const cx<float> p01 = cmake<float>(0.5f * (a2.x + m2.x), 0.5f * (a2.y - m2.y));
+            const cx<float> p10 = cmake<float>(0.5f * (a2.y + m2.y), 0.5f * (m2.x - a2.x));
+            const cx<float> f00 = cmake<float>((float)(g00[q].x * dr0), (float)(g00[q].y * dr0));
+            const cx<float> f01 = cmake<float>((float)(g01[q].x * dr0), (float)(g01[q].y * dr0));
+            const cx<float> f10 = cmake<float>((float)(g10[q].x * dr1), (float)(g10[q].y * dr1));
+            const cx<float> f11 = cmake<float>((float)(g11[q].x * dr1), (float)(g11[q].y * dr1));
+            // dG' = G' [E]+
+            cx<float> d00 = cadd(cmul(f00, p00), cmul(f01, p10));
+            cx<float> d01 = cadd(cmul(f00, p01), cmul(f01, p11));
+            cx<float> d10 = cadd(cmul(f10, p00), cmul(f11, p10));
+            cx<float> d11 = cadd(cmul(f10, p01), cmul(f11, p11));
+            err_r0 = fmaxf(err_r0, fmaxf(d00.x * d00.x + d00.y * d00.y, d01.x * d01.x + d01.y * d01.y));
+            err_r1 = fmaxf(err_r1, fmaxf(d10.x * d10.x + d10.y * d10.y, d11.x * d11.x + d11.y * d11.y));
+            c00 = fmaxf(c00, f00.x * f00.x + f00.y * f00.y);
+            c10 = fmaxf(c10, f10.x * f10.x + f10.y * f10.y);
+            c01m = fmaxf(c01m, f01.x * f01.x + f01.y * f01.y);
+            c11m = fmaxf(c11m, f11.x * f11.x + f11.y * f11.y);
+            // G += D^-1 dG' (fp64 accumulation)
+            g00[q].x += (double)d00.x * i0; g00[q].y += (double)d00.y * i0;
+            g01[q].x += (double)d01.x * i0; g01[q].y += (double)d01.y * i0;
+            g10[q].x += (double)d10.x * i1; g10[q].y += (double)d10.y * i1;
+            g11[q].x += (double)d11.x * i1; g11[q].y += (double)d11.y * i1;
             // the update with its constant-matrix part G (P0 - I) removed
-            d00.x -= h00 * g00[q].x; d00.y -= h00 * g00[q].y;
-            d10.x -= h00 * g10[q].x; d10.y -= h00 * g10[q].y;
-            d01.x -= h01 * g00[q].x + h11 * g01[q].x; d01.y -= h01 * g00[q].y + h11 * g01[q].y;
-            d11.x -= h01 * g10[q].x + h11 * g11[q].x; d11.y -= h01 * g10[q].y + h11 * g11[q].y;
-            rest2 = fmax(rest2, fmax(fmax(d00.x * d00.x + d00.y * d00.y, d01.x * d01.x + d01.y * d01.y),
-                                     fmax(d10.x * d10.x + d10.y * d10.y, d11.x * d11.x + d11.y * d11.y)));
-            g00[q] = n00; g01[q] = n01; g10[q] = n10; g11[q] = n11;
+            d00.x -= h00 * f00.x; d00.y -= h00 * f00.y;
+            d10.x -= h00 * f10.x; d10.y -= h00 * f10.y;
+            d01.x -= h01 * f00.x + h11 * f01.x; d01.y -= h01 * f00.y + h11 * f01.y;
+            d11.x -= h01 * f10.x + h11 * f11.x; d11.y -= h01 * f10.y + h11 * f11.y;
+            rest_r0 = fmaxf(rest_r0, fmaxf(d00.x * d00.x + d00.y * d00.y, d01.x * d01.x + d01.y * d01.y));
+            rest_r1 = fmaxf(rest_r1, fmaxf(d10.x * d10.x + d10.y * d10.y, d11.x * d11.x + d11.y * d11.y));
         }
     }
-    stat[0] = err2; stat[1] = rest2; stat[2] = c00; stat[3] = c10; stat[4] = c01m; stat[5] = c11m;
+    const double w0 = i0 * i0, w1 = i1 * i1;
+    stat[0] = fmax((double)err_r0 * w0, (double)err_r1 * w1);
+    stat[1] = fmax((double)rest_r0 * w0, (double)rest_r1 * w1);
+    stat[2] = (double)c00 * w0; stat[3] = (double)c10 * w1; stat[4] = (double)c01m * w0; stat[5] = (double)c11m * w1;
 }
 
 template <int FPT, typename FFT>
@@ -376,13 +406,18 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
     const int fnn = N / 2 + 1;
     __shared__ double lag0_sh[3];
     __shared__ float lag0f_sh[3];
+    // mixed-precision mode runs EVERY FFT in fp32 (fp32 phase + defect-correction iterations): the fp64 ping-pong
+    // buffers and twiddle tables are then not allocated at all (40 KB instead of 88 KB of shared memory at
+    // nfft = 1000, the rest stays L1 for the cross-spectral gathers)
+    const bool lean = p.tw32 && p.mixed;
     cd* ZA = reinterpret_cast<cd*>(smem_raw);
     cd* ZB = ZA + 2 * (size_t)N;
     cd* tws = ZB + 2 * (size_t)N;
     cx<float>* twsf = reinterpret_cast<cx<float>*>(tws + FFT::tw_entries(N));
     cx<float>* ZAf = reinterpret_cast<cx<float>*>(ZA);  // the fp32 phase reuses the fp64 buffers
     cx<float>* ZBf = ZAf + 2 * (size_t)N;
-    FFT::template fill<double>(tws, p.tw, N);
+    if (lean) twsf = ZBf + 2 * (size_t)N;
+    else FFT::template fill<double>(tws, p.tw, N);
     if (p.tw32) FFT::template fill<float>(twsf, p.tw32, N);
     __syncthreads();
     const long long npairs = p.n_pairs;
@@ -454,13 +489,14 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
         if (!flag) {
             bool converged = false;
             int it0 = 0;
+            // row scales D = diag(a00, a11)^-1/2 of the fp32 arithmetic (fp32 phase and defect iterations)
+            const float r0 = (float)(1.0 / sqrt(a00)), r1 = (float)(1.0 / sqrt(a11));
             if (p.tw32 && p.mixed) {
                 // ---- fp32 phase: the same iteration on the row-scaled problem S' = D S D, G' = D G with
                 // D = diag(a00, a11)^-1/2 (the iteration is equivariant under a left diagonal scaling, so
                 // this only keeps every intermediate O(1) in single precision).  It stops as soon as the
                 // update falls below kSwitch (relative), after which fp64 takes over: the fixed point and
                 // the stopping test are decided entirely in fp64.
-                const float r0 = (float)(1.0 / sqrt(a00)), r1 = (float)(1.0 / sqrt(a11));
                 cx<float> f00[FPT], f01[FPT], f10[FPT], f11[FPT];
 #pragma unroll
                 for (int q = 0; q < FPT; ++q) {
@@ -492,8 +528,8 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                 double st[6];
                 const bool defect = p.tw32 && p.mixed;
                 if (defect)
-                    herm_iteration_defect<FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, ZAf, ZBf, p.plan, twsf, N, fnn,
-                                                    lag0f_sh, st);
+                    herm_iteration_defect<FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, r0, r1, ZAf, ZBf, p.plan, twsf, N,
+                                                    fnn, lag0f_sh, st);
                 else
                     herm_iteration<double, FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, 1.0, 1.0, 1.0, ZA, ZB, p.plan, tws, N,
                                                      fnn, lag0_sh, st);
@@ -631,8 +667,10 @@ size_t herm_smem(int nfft) { return (size_t)5 * nfft * sizeof(cd) + (size_t)nfft
 
 template <int FPT, typename FFT>
 int herm_launch(W2Params& p, cudaStream_t st) {
-    const size_t smem = (size_t)(4 * p.nfft + FFT::tw_entries(p.nfft)) * sizeof(cd) +
-                        (size_t)FFT::tw_entries(p.nfft) * sizeof(cx<float>);
+    const bool lean = p.tw32 && p.mixed;
+    const size_t smem = lean ? (size_t)(4 * p.nfft + FFT::tw_entries(p.nfft)) * sizeof(cx<float>)
+                             : (size_t)(4 * p.nfft + FFT::tw_entries(p.nfft)) * sizeof(cd) +
+                                   (size_t)FFT::tw_entries(p.nfft) * sizeof(cx<float>);
     if (smem > 48 * 1024)
         SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));

@@ -44,11 +44,17 @@ __device__ void top_vector_by_squaring(cd* P, cd* Q, int n, cd* vec, double* red
     cd* src = P;
     cd* dst = Q;
     for (int it = 0; it < kMaxSquarings; ++it) {
+        // P is Hermitian: only the upper triangle is evaluated and mirrored (diagonal forced real), which also
+        // keeps the iterate EXACTLY Hermitian -- an anti-Hermitian rounding component (e.g. the imaginary noise of
+        // an fp32-born diagonal, or of a deflated matrix) would otherwise double with every squaring and run away
         for (int e = threadIdx.x; e < nn; e += blockDim.x) {
             const int i = e / n, j = e - i * n;
+            if (j < i) continue;
             cd acc = cmake<double>(0.0, 0.0);
             for (int k = 0; k < n; ++k) acc = cadd(acc, cmul(src[i * n + k], src[k * n + j]));
+            if (i == j) acc.y = 0.0;
             dst[e] = acc;
+            if (i != j) dst[j * n + i] = cconj(acc);
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -293,6 +299,43 @@ extern "C" int sc_global_coherence(const void* csm_c64, int64_t BF, int S, float
         SC_CUDA_OK(cudaFuncSetAttribute(global_coherence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     global_coherence_kernel<<<(unsigned)BF, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float2*>(csm_c64), BF, S, out_value, reinterpret_cast<float2*>(out_vector_c64));
+    SC_LAUNCH_OK();
+    return SC_OK;
+}
+
+
+// Deflation step of global_coherence(max_rank > 1) (connectivity.py:2245-2279 keeps the max_rank largest singular
+// values): C <- C - lambda v v^H removes the eigenpair just found, so that the next call of sc_global_coherence on the
+// same buffer returns the next one.  One thread per matrix element, c64 in place.
+namespace {
+__global__ void deflate_kernel(float2* __restrict__ csm, long long BF, int S, const float* __restrict__ value,
+                               const float2* __restrict__ vec) {
+    const long long nn = (long long)S * S;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < BF * nn;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long bf = e / nn;
+        const int i = (int)((e - bf * nn) / S), j = (int)((e - bf * nn) % S);
+        const float lam = value[bf];
+        const float2 vi = vec[bf * S + i], vj = vec[bf * S + j];
+        float2 c = csm[e];
+        // v_i conj(v_j) with individually rounded products (no FMA contraction): the update of (i, j) is then the
+        // exact conjugate of the update of (j, i) and the deflated matrix stays exactly Hermitian
+        c.x -= lam * __fadd_rn(__fmul_rn(vi.x, vj.x), __fmul_rn(vi.y, vj.y));
+        c.y -= lam * __fadd_rn(__fmul_rn(vi.y, vj.x), -__fmul_rn(vi.x, vj.y));
+        csm[e] = c;
+    }
+}
+}  // namespace
+
+extern "C" int sc_hermitian_deflate(void* csm_c64, int64_t BF, int S, const float* value, const void* vector_c64,
+                                    void* stream) {
+    SC_CHECK_ARG(csm_c64 && value && vector_c64 && BF > 0 && S > 0, "sc_hermitian_deflate: bad argument");
+    const long long total = BF * (long long)S * S;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sc_num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    deflate_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<float2*>(csm_c64), BF, S, value, reinterpret_cast<const float2*>(vector_c64));
     SC_LAUNCH_OK();
     return SC_OK;
 }

@@ -143,21 +143,25 @@ def agree(group, row, device, time_reduced=False):
 
 
 def plan_window_chunks(n_windows, per_window_bytes, max_chunk_bytes, world=1, multiple_of_world=False,
-                       shrink_tail=False):
+                       shrink_tail=False, grow_head=False):
     """Window ranges [(w0, w1), ...] of the streaming pass.  ``per_window_bytes`` must be a value every rank of a
     reduce group agrees on (GroupState), so that all ranks issue the same sequence of collectives.  With
     ``multiple_of_world`` (reduce_scatter along the window axis) full chunks hold a multiple of ``world`` windows.
     ``shrink_tail``: the last chunks shrink geometrically so that the final device->host copy, which nothing can
-    overlap, is small (host output, single GPU)."""
+    overlap, is small (host output, single GPU).  ``grow_head``: the first chunks grow geometrically (1, 2, 4, ...
+    windows) so that the first transform only waits for the first slab of a host->device copy that is still
+    streaming in (host input)."""
     n_windows = int(n_windows)
     wc = max(1, min(n_windows, int(max_chunk_bytes) // max(int(per_window_bytes), 1)))
     if multiple_of_world and world > 1:
         wc = max(world, wc - wc % world)
-    bounds, w0 = [], 0
+    bounds, w0, head = [], 0, 1
     while w0 < n_windows:
         left = n_windows - w0
         size = min(wc, left)
-        if shrink_tail and left <= wc and left > 1:
+        if grow_head and head < size:
+            size, head = head, head * 2
+        elif shrink_tail and left <= wc and left > 1:
             size = (left + 1) // 2
         bounds.append((w0, w0 + size))
         w0 += size

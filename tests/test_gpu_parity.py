@@ -66,7 +66,7 @@ def test_multitaper_fft_long_window_workspace_path(sc):
     m = sc.Multitaper(x, sampling_frequency=fs, time_halfbandwidth_product=2)
     taps = O.dpss_tapers(n, 2, 3, fs)
     ref = O.multitaper_fft(x, fs, taps, n, n, m.n_fft_samples)
-    assert_parity(m.fft().cpu().numpy(), ref, 2e-5, "long window")
+    assert_parity(m.fft().cpu().numpy(), ref, TOL, "long window")
 
 
 @pytest.mark.parametrize("shape", [(1000, 4, 8), (2000, 3, 17), (360, 2, 33)])
@@ -89,9 +89,10 @@ GOLDEN_MEASURES = ["power", "coherency", "coherence_magnitude", "coherence_phase
                    "phase_locking_value", "phase_lag_index", "weighted_phase_lag_index",
                    "debiased_squared_phase_lag_index", "debiased_squared_weighted_phase_lag_index",
                    "pairwise_phase_consistency"]
-# measures with a removable singularity / cancellation get a looser scale-normalised bound
-LOOSE = {"coherence_phase": 2e-4, "debiased_squared_weighted_phase_lag_index": 2e-4,
-         "debiased_squared_phase_lag_index": 2e-5, "pairwise_phase_consistency": 2e-5}
+# Every measure is held to the 1e-5 contract (round-1's looser bounds for the debiased estimators and the pairwise
+# phase consistency were not needed: achieved errors are <= 8.6e-6, profiles/r02_parity_margins.tsv).  The coherence
+# PHASE is an angle: compared modulo 2 pi, absolute, in radians (its conditioning is 1/|coherency|: 5e-5 rad).
+LOOSE = {"coherence_phase": 5e-5}
 
 
 @pytest.mark.parametrize("et", list(O.EXPECTATION_AXES))
@@ -107,6 +108,10 @@ def test_measures_from_coefficients_golden(sc, et):
         if name == "coherence_phase":  # +pi / -pi are the same angle
             d = np.angle(np.exp(1j * (got[name] - ref)))
             assert np.array_equal(np.isnan(d), np.isnan(ref))
+            import os
+            if os.environ.get("SC_PARITY_LOG"):
+                with open(os.environ["SC_PARITY_LOG"], "a") as fh:
+                    fh.write(f"{et}/coherence_phase [rad]\t{np.nanmax(np.abs(d)):.3e}\t{LOOSE[name]:.1e}\n")
             assert np.nanmax(np.abs(d)) < LOOSE[name]
             continue
         assert_parity(got[name], ref, LOOSE.get(name, TOL), f"{et}/{name}")
@@ -422,7 +427,7 @@ def test_mvar_family_from_coefficients_golden(sc):
     assert_parity(c._noise_covariance, mv["noise_covariance"], TOL, "Sigma")
     assert_parity(c._MVAR_Fourier_coefficients, mv["mvar_fourier_coefficients"], TOL, "A")
     for name in MVAR:
-        assert_parity(getattr(c, name)(), mv[name], 2e-5 if "direct_directed" in name else TOL, name)
+        assert_parity(getattr(c, name)(), mv[name], TOL, name)
 
 
 def test_mvar_family_from_multitaper_golden(sc):
@@ -432,7 +437,7 @@ def test_mvar_family_from_multitaper_golden(sc):
     c = sc.Connectivity.from_multitaper(m)   # real-series path: half spectrum, hermitian Wilson
     assert_parity(c._transfer_function, mv["transfer_function"], TOL, "H")
     for name in MVAR:
-        assert_parity(getattr(c, name)(), mv[name], 2e-5 if "direct_directed" in name else TOL, name)
+        assert_parity(getattr(c, name)(), mv[name], TOL, name)
     assert int(c.last_wilson_flags.sum()) == 0
 
 
@@ -481,7 +486,7 @@ def test_canonical_coherence_larger_groups_vs_oracle(sc):
     coef = O.multitaper_fft(x.astype(np.float32).astype(np.float64), fs, O.dpss_tapers(500, 3, 5, fs), 500, 500, 500)
     ref, ref_lab = O.canonical_coherence(coef, labels)
     assert np.array_equal(lab, ref_lab)
-    assert_parity(cc, ref, 2e-5, "canonical coherence, 4 ragged groups")
+    assert_parity(cc, ref, TOL, "canonical coherence, 4 ragged groups")
     assert np.all((cc[~np.isnan(cc)] >= 0) & (cc[~np.isnan(cc)] <= 1 + 1e-5))
     sym = np.swapaxes(cc, -1, -2)
     assert np.array_equal(np.isnan(cc), np.isnan(sym)) and np.nanmax(np.abs(cc - sym)) == 0
@@ -607,9 +612,9 @@ def test_granger_and_mvar_general_two_sided_coefficients(sc):
     csm, pw = O.expected_csm(coef), O.power(coef)
     ref, its = O.pairwise_granger(csm, pw, return_iterations=True)
     got = c.pairwise_spectral_granger_prediction()
-    assert_parity(got, ref, 2e-5, "granger, general two-sided")
+    assert_parity(got, ref, TOL, "granger, general two-sided")
     h, sigma = O.mvar_transfer_function(csm)
-    assert_parity(c.directed_transfer_function(), O.directed_transfer_function(h), 2e-5, "DTF, general two-sided")
+    assert_parity(c.directed_transfer_function(), O.directed_transfer_function(h), TOL, "DTF, general two-sided")
 
 
 # --------------------------------------------------------------------------- #
