@@ -197,14 +197,17 @@ int64_t sc_wilson_general_workspace_bytes(int64_t B, int F, int S);
  *                    the noise covariance H0 H0^T (f64 [B][S][S], may be NULL); lambda is the caller's
  *                    Tikhonov term 1e-12 * mean(H0^2) over all windows (:1742-1746)
  *  sc_mvar_inverse   A = (H + lambda I)^-1 per (b, f): the MVAR Fourier coefficients (:580-588)
+ *  lambda_device (both): NULL, or a DEVICE scalar that overrides ``lambda`` -- the caller can then form the Tikhonov
+ *                    term with a device reduction and needs no host synchronisation between Wilson and the measures
  * workspace (S > 32 only, else NULL/0): sc_mvar_workspace_bytes(B, 2, S) for sc_mvar_transfer,
  * sc_mvar_workspace_bytes(BF, 1, S) for sc_mvar_inverse. */
 int sc_mvar_lag0(const void* g_c128, int64_t B, int F, int nfft, int hermitian_half, int S, double* out_h0,
                  void* stream);
-int sc_mvar_transfer(const void* g_c128, const double* h0, double lambda, int64_t B, int F, int n_freq_out, int S,
-                     void* out_h_c128, double* out_sigma, void* workspace, int64_t workspace_bytes, void* stream);
-int sc_mvar_inverse(const void* h_c128, double lambda, int64_t BF, int S, void* out_a_c128, void* workspace,
-                    int64_t workspace_bytes, void* stream);
+int sc_mvar_transfer(const void* g_c128, const double* h0, double lambda, const double* lambda_device, int64_t B, int F,
+                     int n_freq_out, int S, void* out_h_c128, double* out_sigma, void* workspace, int64_t workspace_bytes,
+                     void* stream);
+int sc_mvar_inverse(const void* h_c128, double lambda, const double* lambda_device, int64_t BF, int S, void* out_a_c128,
+                    void* workspace, int64_t workspace_bytes, void* stream);
 int64_t sc_mvar_workspace_bytes(int64_t B, int F, int S);
 
 /* directed_transfer_function (0), directed_coherence (1), partial_directed_coherence (2),

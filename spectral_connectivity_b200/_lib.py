@@ -39,8 +39,8 @@ SIGNATURES = {
     "sc_wilson": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, c_double, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
     "sc_wilson_general_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "sc_mvar_lag0": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P]),
-    "sc_mvar_transfer": (c_int, [_P, _P, c_double, c_int64, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),
-    "sc_mvar_inverse": (c_int, [_P, c_double, c_int64, c_int, _P, _P, c_int64, _P]),
+    "sc_mvar_transfer": (c_int, [_P, _P, c_double, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, c_int64, _P]),
+    "sc_mvar_inverse": (c_int, [_P, c_double, _P, c_int64, c_int, _P, _P, c_int64, _P]),
     "sc_mvar_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "sc_canonical_coherence": (c_int, [_P, c_int64, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P]),
     "sc_global_coherence": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int64, _P]),

@@ -832,7 +832,9 @@ class Connectivity:
         del csm
         h0 = torch.empty((n_batch, n_sig, n_sig), dtype=torch.float64, device=dev)
         _lib.check(lib.sc_mvar_lag0(_lib.ptr(g), n_batch, n_freq, nfft, herm, n_sig, _lib.ptr(h0), st), "sc_mvar_lag0")
-        lam = TIKHONOV_REGULARIZATION_FACTOR * float((h0 * h0).mean())  # over all windows, connectivity.py:1742-1746
+        # Tikhonov terms (mean over all windows of the batch, connectivity.py:1742-1746, :585) stay on the device: a
+        # scalar tensor passed by pointer, no host synchronisation between Wilson and the measures
+        lam = TIKHONOV_REGULARIZATION_FACTOR * (h0 * h0).mean()
         h = torch.empty((n_batch, fnn, n_sig, n_sig), dtype=torch.complex128, device=dev)
         sigma = torch.empty((n_batch, n_sig, n_sig), dtype=torch.float64, device=dev)
         need = max(lib.sc_mvar_workspace_bytes(n_batch, 2, n_sig), lib.sc_mvar_workspace_bytes(n_batch * fnn, 1, n_sig))
@@ -840,12 +842,14 @@ class Connectivity:
             del ws
             ws = torch.empty(need, dtype=torch.uint8, device=dev)
             ws_bytes = need
-        _lib.check(lib.sc_mvar_transfer(_lib.ptr(g), _lib.ptr(h0), lam, n_batch, n_freq, fnn, n_sig, _lib.ptr(h),
-                                        _lib.ptr(sigma), _lib.ptr(ws), ws_bytes, st), "sc_mvar_transfer")
-        lam_a = TIKHONOV_REGULARIZATION_FACTOR * float((h.real ** 2 + h.imag ** 2).mean())  # connectivity.py:585
+        _lib.check(lib.sc_mvar_transfer(_lib.ptr(g), _lib.ptr(h0), 0.0, _lib.ptr(lam), n_batch, n_freq, fnn, n_sig,
+                                        _lib.ptr(h), _lib.ptr(sigma), _lib.ptr(ws), ws_bytes, st), "sc_mvar_transfer")
+        hr = torch.view_as_real(h)
+        lam_a = TIKHONOV_REGULARIZATION_FACTOR * (hr * hr).sum() / h.numel()
+        del hr
         a = torch.empty_like(h)
-        _lib.check(lib.sc_mvar_inverse(_lib.ptr(h), lam_a, n_batch * fnn, n_sig, _lib.ptr(a), _lib.ptr(ws), ws_bytes, st),
-                   "sc_mvar_inverse")
+        _lib.check(lib.sc_mvar_inverse(_lib.ptr(h), 0.0, _lib.ptr(lam_a), n_batch * fnn, n_sig, _lib.ptr(a), _lib.ptr(ws),
+                                       ws_bytes, st), "sc_mvar_inverse")
         return dict(g=g, h=h, sigma=sigma, a=a, iters=iters, flags=flags, n_batch=n_batch, fnn=fnn, n_sig=n_sig)
 
     def _mvar_warn(self, flags):

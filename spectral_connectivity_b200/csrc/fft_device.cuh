@@ -469,6 +469,87 @@ struct ScStaticConv<R, ScStaticPlan<N, R0, R1, R0>, KCUT, POW> {
     }
 };
 
+// ---- register-resident twiddles ---------------------------------------------------------------------------------
+// When a CTA transforms NB sequences with NB * N / R0 <= nthreads, thread `tid` executes butterfly j = tid % (N/R0)
+// of sequence tid / (N/R0) in EVERY stage of EVERY transform: the twiddle factors it needs -- W^(t k) with
+// k = j % R0 in the middle stages and k = j in the outer stages (R0 == R1 plans) -- never change, so they are loaded
+// once into registers (2 * (R0 - 1) complex values) instead of 9 shared-memory loads per butterfly and stage (31 %
+// of the shared-memory wavefronts of the Wilson iteration, whose FFT passes are shared-memory bound).
+template <typename R, int RADIX> struct ScTwRegs {
+    cx<R> mid[RADIX - 1];    // stage with sub-length LS = R0:   W_N^(t * (j % R0) * N / (R0 * R1)), t = 1 .. R1-1
+    cx<R> outer[RADIX - 1];  // stage with sub-length LS = N/R0: W_N^(t * j),                        t = 1 .. R0-1
+};
+
+template <typename R, int RADIX>
+SC_HD void sc_apply_twiddle_regs(cx<R>* v, const cx<R>* w, bool inv) {
+#pragma unroll
+    for (int t = 1; t < RADIX; ++t) v[t] = cmul(v[t], inv ? cconj(w[t - 1]) : w[t - 1]);
+}
+
+template <typename R, int N, int LS, int RADIX>
+SC_HD void sc_static_item_rt(const cx<R>* src, cx<R>* dst, int j, const cx<R>* w, bool inv) {
+    constexpr int M = N / RADIX;
+    const int k = LS == 1 ? 0 : (LS == M ? j : j % LS);
+    cx<R> v[RADIX];
+#pragma unroll
+    for (int t = 0; t < RADIX; ++t) v[t] = src[j + t * M];
+    if (LS > 1) sc_apply_twiddle_regs<R, RADIX>(v, w, inv);
+    sc_dft<R, RADIX>(v, inv, (const cx<R>*)0, N);
+    const int ob = (j - k) * RADIX + k;
+#pragma unroll
+    for (int q = 0; q < RADIX; ++q) dst[ob + q * LS] = v[q];
+}
+
+// ScStaticConv for R0 == R1 three-stage plans with register twiddles; requires NB * N / R0 <= nthreads.
+template <typename R, int N, int R0, int KCUT> struct ScStaticConvRt {
+    static constexpr int M = N / R0;
+    // twiddles of thread `tid` from the flat table tw[q] = exp(-2 pi i q / N)
+    static SC_HD void load(ScTwRegs<R, R0>& w, const cx<R>* tw, int tid) {
+        const int j = tid % M;
+#pragma unroll
+        for (int t = 1; t < R0; ++t) {
+            w.mid[t - 1] = tw[(t * (j % R0) * (N / (R0 * R0))) % N];
+            w.outer[t - 1] = tw[(t * j) % N];
+        }
+    }
+    template <int NB, typename SYNC, typename WIN>
+    static SC_HD cx<R>* run(cx<R>* a, cx<R>* b, const ScTwRegs<R, R0>& w, int tid, SYNC sync, WIN win) {
+        const bool act = tid < NB * M;
+        const int bb = tid / M, j = tid - bb * M;
+        cx<R>* sa = a + bb * N;
+        cx<R>* sb = b + bb * N;
+        if (act) sc_static_item_rt<R, N, 1, R0>(sa, sb, j, w.mid, true);
+        sync();
+        if (act) sc_static_item_rt<R, N, R0, R0>(sb, sa, j, w.mid, true);
+        sync();
+        if (act) {  // last inverse stage -> window -> first forward stage, in registers (see sc_static_mid_item)
+            constexpr bool HALF = (KCUT % M == 0) && (KCUT / M == R0 / 2) && (R0 % 2 == 0);
+            cx<R> v[R0];
+#pragma unroll
+            for (int t = 0; t < R0; ++t) v[t] = sa[j + t * M];
+            sc_apply_twiddle_regs<R, R0>(v, w.outer, true);
+            sc_dft<R, R0>(v, true, (const cx<R>*)0, N);
+            if (HALF) {
+#pragma unroll
+                for (int q = 0; q < R0 / 2; ++q) v[q] = win(bb, j + q * M, v[q]);
+                sc_dft_lowhalf<R, R0>(v);
+            } else {
+#pragma unroll
+                for (int q = 0; q < R0; ++q) v[q] = (j + q * M < KCUT) ? win(bb, j + q * M, v[q]) : cmake<R>((R)0, (R)0);
+                sc_dft<R, R0>(v, false, (const cx<R>*)0, N);
+            }
+#pragma unroll
+            for (int q = 0; q < R0; ++q) sb[j * R0 + q] = v[q];
+        }
+        sync();
+        if (act) sc_static_item_rt<R, N, R0, R0>(sb, sa, j, w.mid, false);
+        sync();
+        if (act) sc_static_item_rt<R, N, R0 * R0, R0>(sa, sb, j, w.outer, false);
+        sync();
+        return b;
+    }
+};
+
 typedef ScStaticPlan<1000, 10, 10, 10> ScPlan1000;
 typedef ScStaticPlan<120, 10, 4, 3> ScPlan120;
 

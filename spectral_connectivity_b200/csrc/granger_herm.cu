@@ -15,6 +15,8 @@
 //    inverse+forward pair instead of 7;
 //  * the Granger epilogue (transfer function, noise covariance, log ratio) is evaluated from the
 //    registers and written straight into the (B, Fnn, S, S) output.
+#include <stdlib.h>
+
 #include "wilson_common.cuh"
 
 namespace {
@@ -22,6 +24,10 @@ namespace {
 using namespace scw;
 
 constexpr int kMaxF32Iters = 12;     // fp32 phase never runs longer than this
+#ifndef SC_GRANGER_GROUP
+#define SC_GRANGER_GROUP 4
+#endif
+constexpr int kGroup = SC_GRANGER_GROUP;  // consecutive pair indices one CTA handles back to back (sector reuse in L1)
 constexpr double kTailRest = 32.0;   // closed-form tail once the non-constant part of the update is below
                                      // kTailRest * tol: those modes converge quadratically, so what is left of
                                      // them after the update is far below tol (measured deviation from the
@@ -46,7 +52,17 @@ struct CtaSync {
 };
 
 // FFT policies: runtime plan (any length) or a compile-time plan (fft_device.cuh).
+struct NoTwRegs {};  // placeholder of plans without register-resident twiddles
+
+template <typename PLAN> struct PlanR0 { static constexpr int value = 0; };
+template <int N, int R0, int... REST> struct PlanR0<ScStaticPlan<N, R0, REST...>> { static constexpr int value = R0; };
+
 struct DynFft {
+    static constexpr bool kRegTw = false;
+    typedef NoTwRegs TwRegs;
+    static __device__ __forceinline__ void load_regs(TwRegs&, const cx<float>*) {}
+    template <typename WIN>
+    static __device__ __forceinline__ cx<float>* conv2_rt(cx<float>* a, cx<float>*, const TwRegs&, WIN) { return a; }
     static constexpr bool kPrefetch = false;  // runtime-plan kernels are at the register cap already
     template <typename R> struct Fused { static constexpr bool value = false; };
     template <typename R, typename WIN>
@@ -62,7 +78,30 @@ struct DynFft {
         return sc_cta_fft<R, true>(a, b, 2, plan.n, plan, tws, inv);
     }
 };
-template <typename PLAN> struct StatFft {
+template <typename PLAN, bool RT = ScStaticConv<float, PLAN, (PLAN::n + 1) / 2, false>::supported &&
+                                   (PlanR0<PLAN>::value > 0) && (2 * (PLAN::n / (PlanR0<PLAN>::value > 0 ? PlanR0<PLAN>::value : 1)) <= kThreads)>
+struct StatFftRegs {
+    static constexpr bool kRegTw = false;
+    typedef NoTwRegs TwRegs;
+    static __device__ __forceinline__ void load_regs(TwRegs&, const cx<float>*) {}
+    template <typename WIN>
+    static __device__ __forceinline__ cx<float>* conv2_rt(cx<float>* a, cx<float>*, const TwRegs&, WIN) { return a; }
+};
+// three-stage plans with equal radices whose two packed sequences need at most one butterfly per thread and stage:
+// the fp32 twiddles live in registers (fft_device.cuh: ScStaticConvRt)
+template <typename PLAN> struct StatFftRegs<PLAN, true> {
+    static constexpr bool kRegTw = true;
+    static constexpr int R0 = PlanR0<PLAN>::value;
+    typedef ScTwRegs<float, R0> TwRegs;
+    typedef ScStaticConvRt<float, PLAN::n, R0, (PLAN::n + 1) / 2> Conv;
+    static __device__ __forceinline__ void load_regs(TwRegs& w, const cx<float>* tw_flat) { Conv::load(w, tw_flat, threadIdx.x); }
+    template <typename WIN>
+    static __device__ __forceinline__ cx<float>* conv2_rt(cx<float>* a, cx<float>* b, const TwRegs& w, WIN win) {
+        return Conv::template run<2>(a, b, w, threadIdx.x, CtaSync(), win);
+    }
+};
+
+template <typename PLAN> struct StatFft : StatFftRegs<PLAN> {
     static constexpr bool kPrefetch = true;  // fetch the next problem's spectrum under the epilogue
     static constexpr int kCut = (PLAN::n + 1) / 2;  // the plus operator keeps lags [0, kCut)
     template <typename R> struct Fused {
@@ -137,12 +176,12 @@ template <typename R> struct PlusWindow {
 // causal factor (the update with the constant-matrix mode removed, see granger_herm_kernel),
 // stat[2..5] = max over this thread's bins of |g00|^2, |g10|^2, |g01|^2, |g11|^2 of G_prev;
 // lag0[0..2] = lag-0 residual e00, e01, e11 of G^-1 S G^-H - I (real for real time series).
-template <typename R, int FPT, typename FFT>
+template <typename R, int FPT, typename FFT, bool RT = false>
 __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[FPT], cx<R> (&g10)[FPT],
                                                cx<R> (&g11)[FPT], const float (&s00)[FPT], const float (&s11)[FPT],
                                                const float2 (&s01)[FPT], R k00, R k11, R k01, cx<R>* ZA, cx<R>* ZB,
                                                const ScFftPlan& plan, const cx<R>* tw, int N, int fnn,
-                                               R* lag0, R (&stat)[6]) {
+                                               R* lag0, R (&stat)[6], const typename FFT::TwRegs* twr = nullptr) {
     // ---- linear predictor (mpd.py:218-224), Hermitian: b00, b11 real, b10 = conj(b01) ----
 #pragma unroll
     for (int q = 0; q < FPT; ++q) {
@@ -185,7 +224,9 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
     // ---- plus operator (mpd.py:129-142) between the inverse and the forward transforms ----
     const PlusWindow<R> win = {(R)1 / (R)N, lag0};
     const cx<R>* Q;
-    if (FFT::template Fused<R>::value) {
+    if constexpr (RT && sizeof(R) == 4) {
+        Q = FFT::conv2_rt(ZA, ZB, *twr, win);
+    } else if (FFT::template Fused<R>::value) {
         Q = FFT::template conv2<R>(ZA, ZB, tw, win);
     } else {
         cx<R>* c = FFT::template run2<R>(ZA, ZB, plan, tw, true);
@@ -273,30 +314,53 @@ struct PlusWindowDefect {
 // takes over, 1e-6 at the last iteration) moves G by ~1e-11 absolute, three orders below the 1e-8 stopping
 // tolerance.  G itself is accumulated in fp64 (G += D^-1 dG').  Same outputs as herm_iteration<double>
 // (stat[], lag0[] as float); the maxima are taken per row in scaled units and unscaled once per thread.
-template <int FPT, typename FFT>
-__device__ __forceinline__ void herm_iteration_defect(cd (&g00)[FPT], cd (&g01)[FPT], cd (&g10)[FPT], cd (&g11)[FPT],
+// Where the fp64 factor G of the defect iterations lives: in registers (arrays indexed by the thread's bin slot q), or
+// in shared memory ([4][fnn] complex doubles, bin-major: consecutive threads touch consecutive 16-byte slots, each
+// thread only ever touches its own bins).  The shared-memory variant lets the kernel run under an 85-register cap
+// (3 CTAs per SM): the fp32 phase, where nearly all iterations happen, does not pay registers for fp64 state.
+template <int FPT> struct GRegs {
+    cd (&g00)[FPT]; cd (&g01)[FPT]; cd (&g10)[FPT]; cd (&g11)[FPT];
+    __device__ __forceinline__ void load(int q, int, cd& a, cd& b, cd& c, cd& d) const { a = g00[q]; b = g01[q]; c = g10[q]; d = g11[q]; }
+    __device__ __forceinline__ void store(int q, int, cd a, cd b, cd c, cd d) const { g00[q] = a; g01[q] = b; g10[q] = c; g11[q] = d; }
+};
+struct GSmem {
+    cd* g;       // [4][stride]
+    int stride;
+    __device__ __forceinline__ void load(int, int f, cd& a, cd& b, cd& c, cd& d) const {
+        a = g[f]; b = g[stride + f]; c = g[2 * stride + f]; d = g[3 * stride + f];
+    }
+    __device__ __forceinline__ void store(int, int f, cd a, cd b, cd c, cd d) const {
+        g[f] = a; g[stride + f] = b; g[2 * stride + f] = c; g[3 * stride + f] = d;
+    }
+};
+
+template <int FPT, typename FFT, typename GACC, bool RT = false>
+__device__ __forceinline__ void herm_iteration_defect(const GACC gacc,
                                                       const float (&s00)[FPT], const float (&s11)[FPT],
                                                       const float2 (&s01)[FPT], float r0, float r1, cx<float>* ZA,
                                                       cx<float>* ZB, const ScFftPlan& plan, const cx<float>* tw, int N,
-                                                      int fnn, float* lag0, double (&stat)[6]) {
+                                                      int fnn, float* lag0, double (&stat)[6],
+                                                      const typename FFT::TwRegs* twr = nullptr) {
     const double dr0 = (double)r0, dr1 = (double)r1;
     const double k00 = dr0 * dr0, k11 = dr1 * dr1, k01 = dr0 * dr1;
 #pragma unroll
     for (int q = 0; q < FPT; ++q) {
         const int f = threadIdx.x + q * kThreads;
         if (f < fnn) {
+            cd G00, G01, G10, G11;
+            gacc.load(q, f, G00, G01, G10, G11);
             // residual R = S - G G^H in fp64, scaled: R' = D R D
-            const double n00 = g00[q].x * g00[q].x + g00[q].y * g00[q].y + g01[q].x * g01[q].x + g01[q].y * g01[q].y;
-            const double n11 = g10[q].x * g10[q].x + g10[q].y * g10[q].y + g11[q].x * g11[q].x + g11[q].y * g11[q].y;
-            const double n01x = g00[q].x * g10[q].x + g00[q].y * g10[q].y + g01[q].x * g11[q].x + g01[q].y * g11[q].y;
-            const double n01y = g00[q].y * g10[q].x - g00[q].x * g10[q].y + g01[q].y * g11[q].x - g01[q].x * g11[q].y;
+            const double n00 = G00.x * G00.x + G00.y * G00.y + G01.x * G01.x + G01.y * G01.y;
+            const double n11 = G10.x * G10.x + G10.y * G10.y + G11.x * G11.x + G11.y * G11.y;
+            const double n01x = G00.x * G10.x + G00.y * G10.y + G01.x * G11.x + G01.y * G11.y;
+            const double n01y = G00.y * G10.x - G00.x * G10.y + G01.y * G11.x - G01.x * G11.y;
             const float a = (float)(((double)s00[q] - n00) * k00), d = (float)(((double)s11[q] - n11) * k11);
             const cx<float> c = cmake<float>((float)(((double)s01[q].x - n01x) * k01), (float)(((double)s01[q].y - n01y) * k01));
             // scaled factor G' = D G and its inverse in fp32
-            const cx<float> f00 = cmake<float>((float)(g00[q].x * dr0), (float)(g00[q].y * dr0));
-            const cx<float> f01 = cmake<float>((float)(g01[q].x * dr0), (float)(g01[q].y * dr0));
-            const cx<float> f10 = cmake<float>((float)(g10[q].x * dr1), (float)(g10[q].y * dr1));
-            const cx<float> f11 = cmake<float>((float)(g11[q].x * dr1), (float)(g11[q].y * dr1));
+            const cx<float> f00 = cmake<float>((float)(G00.x * dr0), (float)(G00.y * dr0));
+            const cx<float> f01 = cmake<float>((float)(G01.x * dr0), (float)(G01.y * dr0));
+            const cx<float> f10 = cmake<float>((float)(G10.x * dr1), (float)(G10.y * dr1));
+            const cx<float> f11 = cmake<float>((float)(G11.x * dr1), (float)(G11.y * dr1));
             const cx<float> det = csub(cmul(f00, f11), cmul(f01, f10));
             const float dn = 1.0f / (det.x * det.x + det.y * det.y);
             const cx<float> idet = cmake<float>(det.x * dn, -det.y * dn);
@@ -325,7 +389,9 @@ __device__ __forceinline__ void herm_iteration_defect(cd (&g00)[FPT], cd (&g01)[
     __syncthreads();
     const PlusWindowDefect win = {1.0f / (float)N, lag0};
     const cx<float>* Q;
-    if (FFT::template Fused<float>::value) {
+    if constexpr (RT) {
+        Q = FFT::conv2_rt(ZA, ZB, *twr, win);
+    } else if (FFT::template Fused<float>::value) {
         Q = FFT::template conv2<float>(ZA, ZB, tw, win);
     } else {
         cx<float>* c = FFT::template run2<float>(ZA, ZB, plan, tw, true);
@@ -358,10 +424,12 @@ __device__ __forceinline__ void herm_iteration_defect(cd (&g00)[FPT], cd (&g01)[
             const cx<float> p11 = cmake<float>(0.5f * (a1.y + m1.y), 0.5f * (m1.x - a1.x));
             const cx<float> p01 = cmake<float>(0.5f * (a2.x + m2.x), 0.5f * (a2.y - m2.y));
             const cx<float> p10 = cmake<float>(0.5f * (a2.y + m2.y), 0.5f * (m2.x - a2.x));
-            const cx<float> f00 = cmake<float>((float)(g00[q].x * dr0), (float)(g00[q].y * dr0));
-            const cx<float> f01 = cmake<float>((float)(g01[q].x * dr0), (float)(g01[q].y * dr0));
-            const cx<float> f10 = cmake<float>((float)(g10[q].x * dr1), (float)(g10[q].y * dr1));
-            const cx<float> f11 = cmake<float>((float)(g11[q].x * dr1), (float)(g11[q].y * dr1));
+            cd G00, G01, G10, G11;
+            gacc.load(q, f, G00, G01, G10, G11);
+            const cx<float> f00 = cmake<float>((float)(G00.x * dr0), (float)(G00.y * dr0));
+            const cx<float> f01 = cmake<float>((float)(G01.x * dr0), (float)(G01.y * dr0));
+            const cx<float> f10 = cmake<float>((float)(G10.x * dr1), (float)(G10.y * dr1));
+            const cx<float> f11 = cmake<float>((float)(G11.x * dr1), (float)(G11.y * dr1));
             // dG' = G' [E]+
             cx<float> d00 = cadd(cmul(f00, p00), cmul(f01, p10));
             cx<float> d01 = cadd(cmul(f00, p01), cmul(f01, p11));
@@ -374,10 +442,11 @@ __device__ __forceinline__ void herm_iteration_defect(cd (&g00)[FPT], cd (&g01)[
             c01m = fmaxf(c01m, f01.x * f01.x + f01.y * f01.y);
             c11m = fmaxf(c11m, f11.x * f11.x + f11.y * f11.y);
             // G += D^-1 dG' (fp64 accumulation)
-            g00[q].x += (double)d00.x * i0; g00[q].y += (double)d00.y * i0;
-            g01[q].x += (double)d01.x * i0; g01[q].y += (double)d01.y * i0;
-            g10[q].x += (double)d10.x * i1; g10[q].y += (double)d10.y * i1;
-            g11[q].x += (double)d11.x * i1; g11[q].y += (double)d11.y * i1;
+            G00.x += (double)d00.x * i0; G00.y += (double)d00.y * i0;
+            G01.x += (double)d01.x * i0; G01.y += (double)d01.y * i0;
+            G10.x += (double)d10.x * i1; G10.y += (double)d10.y * i1;
+            G11.x += (double)d11.x * i1; G11.y += (double)d11.y * i1;
+            gacc.store(q, f, G00, G01, G10, G11);
             // the update with its constant-matrix part G (P0 - I) removed
             d00.x -= h00 * f00.x; d00.y -= h00 * f00.y;
             d10.x -= h00 * f10.x; d10.y -= h00 * f10.y;
@@ -393,7 +462,14 @@ __device__ __forceinline__ void herm_iteration_defect(cd (&g00)[FPT], cd (&g01)[
     stat[2] = (double)c00 * w0; stat[3] = (double)c10 * w1; stat[4] = (double)c01m * w0; stat[5] = (double)c11m * w1;
 }
 
-template <int FPT, typename FFT>
+// LEAN = the mixed-precision mode (every FFT in fp32): fp32 ping-pong buffers only, the fp64 factor of the defect
+// iterations in shared memory instead of registers, and -- for plans that support it (nfft = 1000) -- the FFT
+// twiddles of each thread's fixed butterfly in the registers that frees (no twiddle tables in shared memory at all:
+// the iteration's FFT passes are bound by shared-memory wavefronts, 31 % of which were twiddle loads).
+// Measured dead end, kept out: an 85-register cap for 3 CTAs per SM (fp64 factor in shared memory, tables kept)
+// leaves the iterations at the same speed -- they are throughput, not latency bound -- while the 11 KB of L1 that
+// three 72 KB CTAs leave slow the strided cross-spectral gathers down by 2x (profiles/r02_granger_experiments.txt).
+template <int FPT, typename FFT, bool LEAN>
 __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[6 * kWarps];
@@ -409,16 +485,24 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
     // mixed-precision mode runs EVERY FFT in fp32 (fp32 phase + defect-correction iterations): the fp64 ping-pong
     // buffers and twiddle tables are then not allocated at all (40 KB instead of 88 KB of shared memory at
     // nfft = 1000, the rest stays L1 for the cross-spectral gathers)
-    const bool lean = p.tw32 && p.mixed;
+    constexpr bool lean = LEAN;
     cd* ZA = reinterpret_cast<cd*>(smem_raw);
     cd* ZB = ZA + 2 * (size_t)N;
     cd* tws = ZB + 2 * (size_t)N;
     cx<float>* twsf = reinterpret_cast<cx<float>*>(tws + FFT::tw_entries(N));
     cx<float>* ZAf = reinterpret_cast<cx<float>*>(ZA);  // the fp32 phase reuses the fp64 buffers
     cx<float>* ZBf = ZAf + 2 * (size_t)N;
+    constexpr bool kRT = LEAN && FFT::kRegTw;  // fp32 twiddles in registers: no shared-memory tables
     if (lean) twsf = ZBf + 2 * (size_t)N;
     else FFT::template fill<double>(tws, p.tw, N);
-    if (p.tw32) FFT::template fill<float>(twsf, p.tw32, N);
+    // LEAN: fp64 factor [4][fnn] behind the fp32 buffers (and tables, if any), 16-byte aligned
+    const int gstride = fnn;
+    cd* G64 = reinterpret_cast<cd*>(
+        smem_raw + ((((size_t)4 * N + (kRT ? 0 : FFT::tw_entries(N))) * sizeof(cx<float>) + 15) & ~(size_t)15));
+    const GSmem gsm = {G64, gstride};
+    typename FFT::TwRegs twr;
+    if constexpr (kRT) FFT::load_regs(twr, p.tw32);
+    else if (p.tw32) FFT::template fill<float>(twsf, p.tw32, N);
     __syncthreads();
     const long long npairs = p.n_pairs;
     const long long nprob = p.B * npairs;
@@ -456,12 +540,20 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
     };
     long long b = 0, pk = 0, nb_ = 0, npk = 0;
     int pi = 0, pj = 0, npi = 0, npj = 0;
-    if (blockIdx.x < nprob) {
-        pair_of(blockIdx.x, b, pk, pi, pj);
+    // Problem order: a CTA works through GROUPS of kGroup consecutive pair indices -- (i, j), (i, j+1), ... of one
+    // window.  Their cross-spectral entries S_ij sit in the same 32-byte sectors (4 pairs each), S_ii is the same
+    // element, and their power / output columns share sectors too, so after the first problem of a group the strided
+    // gathers below (501 bins x 3 entries, every one in a different matrix) mostly hit the L1 the kernel leaves free.
+    const long long first = (long long)blockIdx.x * kGroup;
+    auto next_prob = [&](long long pr) {
+        return ((pr + 1) % kGroup != 0) ? pr + 1 : (pr / kGroup + gridDim.x) * kGroup;
+    };
+    if (first < nprob) {
+        pair_of(first, b, pk, pi, pj);
         load_s(b, pi, pj);
     }
-    for (long long prob = blockIdx.x; prob < nprob; prob += gridDim.x, b = nb_, pk = npk, pi = npi, pj = npj) {
-        if (!FFT::kPrefetch && prob != blockIdx.x) {
+    for (long long prob = first; prob < nprob; prob = next_prob(prob), b = nb_, pk = npk, pi = npi, pj = npj) {
+        if (!FFT::kPrefetch && prob != first) {
             pair_of(prob, b, pk, pi, pj);
             load_s(b, pi, pj);
         }
@@ -480,12 +572,23 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
         const double l00 = sqrt(a00), l10 = a10 / l00, d11 = a11 - l10 * l10, l11 = sqrt(d11);
         int flag = 0, it_done = 0;
         if (!(a00 > 0.0) || !(d11 > 0.0) || !isfinite(l00) || !isfinite(l11)) flag = SC_FLAG_NOT_SPD;
-        cd g00[FPT], g01[FPT], g10[FPT], g11[FPT];
+        constexpr int GN = LEAN ? 1 : FPT;  // LEAN keeps the fp64 factor in shared memory (G64)
+        cd g00[GN], g01[GN], g10[GN], g11[GN];
 #pragma unroll
-        for (int q = 0; q < FPT; ++q) {
+        for (int q = 0; q < GN; ++q) {
             g00[q] = cmake<double>(l00, 0.0); g01[q] = cmake<double>(l10, 0.0);
             g10[q] = cmake<double>(0.0, 0.0); g11[q] = cmake<double>(l11, 0.0);
         }
+        const GRegs<GN> greg = {g00, g01, g10, g11};
+        // this thread's bin slot q (frequency f) of the fp64 factor, wherever it lives
+        auto gload = [&](int q, int f, cd& a_, cd& b_, cd& c_, cd& d_) {
+            if constexpr (LEAN) gsm.load(q, f, a_, b_, c_, d_);
+            else greg.load(q, f, a_, b_, c_, d_);
+        };
+        auto gstore = [&](int q, int f, cd a_, cd b_, cd c_, cd d_) {
+            if constexpr (LEAN) gsm.store(q, f, a_, b_, c_, d_);
+            else greg.store(q, f, a_, b_, c_, d_);
+        };
         if (!flag) {
             bool converged = false;
             int it0 = 0;
@@ -506,8 +609,8 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                 const int cap = p.max_iter < kMaxF32Iters ? p.max_iter : kMaxF32Iters;
                 for (; it0 < cap; ++it0) {
                     float stf[6];
-                    herm_iteration<float, FPT, FFT>(f00, f01, f10, f11, s00, s11, s01, r0 * r0, r1 * r1, r0 * r1, ZAf, ZBf,
-                                                    p.plan, twsf, N, fnn, lag0f_sh, stf);
+                    herm_iteration<float, FPT, FFT, kRT>(f00, f01, f10, f11, s00, s11, s01, r0 * r0, r1 * r1, r0 * r1, ZAf,
+                                                         ZBf, p.plan, twsf, N, fnn, lag0f_sh, stf, &twr);
                     // update minus its constant-matrix (tail) part; the barrier inside also fences the buffers
                     const float errf = sqrtf(block_max_nonneg(stf[1], redf, phase_f));
                     if (errf < kSwitch) {
@@ -518,21 +621,28 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                 const double u0 = sqrt(a00), u1 = sqrt(a11);
 #pragma unroll
                 for (int q = 0; q < FPT; ++q) {
-                    g00[q] = cmake<double>(f00[q].x * u0, f00[q].y * u0); g01[q] = cmake<double>(f01[q].x * u0, f01[q].y * u0);
-                    g10[q] = cmake<double>(f10[q].x * u1, f10[q].y * u1); g11[q] = cmake<double>(f11[q].x * u1, f11[q].y * u1);
+                    const int f = threadIdx.x + q * kThreads;
+                    if (f < fnn || !LEAN)
+                        gstore(q, f, cmake<double>(f00[q].x * u0, f00[q].y * u0), cmake<double>(f01[q].x * u0, f01[q].y * u0),
+                               cmake<double>(f10[q].x * u1, f10[q].y * u1), cmake<double>(f11[q].x * u1, f11[q].y * u1));
                 }
                 it_done = it0;
                 cnt_f32 += it0;
             }
             for (int it = it0; it < p.max_iter && !converged; ++it) {
                 double st[6];
-                const bool defect = p.tw32 && p.mixed;
-                if (defect)
-                    herm_iteration_defect<FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, r0, r1, ZAf, ZBf, p.plan, twsf, N,
-                                                    fnn, lag0f_sh, st);
-                else
-                    herm_iteration<double, FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, 1.0, 1.0, 1.0, ZA, ZB, p.plan, tws, N,
-                                                     fnn, lag0_sh, st);
+                const bool defect = LEAN || (p.tw32 && p.mixed);
+                if constexpr (LEAN) {
+                    herm_iteration_defect<FPT, FFT, GSmem, kRT>(gsm, s00, s11, s01, r0, r1, ZAf, ZBf, p.plan, twsf, N, fnn,
+                                                                lag0f_sh, st, &twr);
+                } else {
+                    if (defect)
+                        herm_iteration_defect<FPT, FFT>(greg, s00, s11, s01, r0, r1, ZAf, ZBf, p.plan, twsf, N, fnn,
+                                                        lag0f_sh, st);
+                    else
+                        herm_iteration<double, FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, 1.0, 1.0, 1.0, ZA, ZB, p.plan, tws,
+                                                         N, fnn, lag0_sh, st);
+                }
                 block_maxn_nonneg<6>(st, redd, phase_d);  // also fences ZA/ZB reuse
                 const double err = sqrt(st[0]);
                 it_done = it + 1;
@@ -588,9 +698,14 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                     converged = tail_it[1] != 0;
 #pragma unroll
                     for (int q = 0; q < FPT; ++q) {
-                        g01[q].x = g00[q].x * tb + g01[q].x * td; g01[q].y = g00[q].y * tb + g01[q].y * td;
-                        g11[q].x = g10[q].x * tb + g11[q].x * td; g11[q].y = g10[q].y * tb + g11[q].y * td;
-                        g00[q].x *= ta; g00[q].y *= ta; g10[q].x *= ta; g10[q].y *= ta;
+                        const int f = threadIdx.x + q * kThreads;
+                        if (f >= fnn && LEAN) continue;
+                        cd A, B, C, D;
+                        gload(q, f, A, B, C, D);
+                        B.x = A.x * tb + B.x * td; B.y = A.y * tb + B.y * td;
+                        D.x = C.x * tb + D.x * td; D.y = C.y * tb + D.y * td;
+                        A.x *= ta; A.y *= ta; C.x *= ta; C.y *= ta;
+                        gstore(q, f, A, B, C, D);
                     }
                     break;
                 }
@@ -605,8 +720,8 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
         // the spectrum registers are free now: fetch the next problem's S under the epilogue
         const int cpi = pi, cpj = pj;
         const long long cb = b;
-        if (FFT::kPrefetch && prob + gridDim.x < nprob) {
-            pair_of(prob + gridDim.x, nb_, npk, npi, npj);
+        if (FFT::kPrefetch && next_prob(prob) < nprob) {
+            pair_of(next_prob(prob), nb_, npk, npi, npj);
             load_s(nb_, npi, npj);
         }
         float* out = reinterpret_cast<float*>(p.out);
@@ -629,7 +744,9 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
                 pw_i[q] = __ldg(&p.power[((size_t)cb * p.F + f) * p.S + cpi]);
                 pw_j[q] = __ldg(&p.power[((size_t)cb * p.F + f) * p.S + cpj]);
                 const double w = (f == 0 || 2 * f == N) ? 1.0 : 2.0;
-                h[0] += w * g00[q].x; h[1] += w * g01[q].x; h[2] += w * g10[q].x; h[3] += w * g11[q].x;
+                cd A, B, C, D;
+                gload(q, f, A, B, C, D);
+                h[0] += w * A.x; h[1] += w * B.x; h[2] += w * C.x; h[3] += w * D.x;
             }
         }
         block_sum<4>(h, red);
@@ -645,8 +762,10 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
         for (int q = 0; q < FPT; ++q) {
             const int f = threadIdx.x + q * kThreads;
             if (f < fnn) {
-                const cd t01 = cmake<double>(g00[q].x * v01 + g01[q].x * v11, g00[q].y * v01 + g01[q].y * v11);
-                const cd t10 = cmake<double>(g10[q].x * v00 + g11[q].x * v10, g10[q].y * v00 + g11[q].y * v10);
+                cd A, B, C, D;
+                gload(q, f, A, B, C, D);
+                const cd t01 = cmake<double>(A.x * v01 + B.x * v11, A.y * v01 + B.y * v11);
+                const cd t10 = cmake<double>(C.x * v00 + D.x * v10, C.y * v00 + D.y * v10);
                 const float gc01 = log_ratio((double)pw_i[q], r01 * (t01.x * t01.x + t01.y * t01.y));
                 const float gc10 = log_ratio((double)pw_j[q], r10 * (t10.x * t10.x + t10.y * t10.y));
                 float* m = out + ((size_t)cb * fnn + f) * p.S * p.S;
@@ -665,24 +784,42 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
 
 size_t herm_smem(int nfft) { return (size_t)5 * nfft * sizeof(cd) + (size_t)nfft * 8; }  // ZA, ZB, twiddles (f64 + f32)
 
-template <int FPT, typename FFT>
-int herm_launch(W2Params& p, cudaStream_t st) {
-    const bool lean = p.tw32 && p.mixed;
-    const size_t smem = lean ? (size_t)(4 * p.nfft + FFT::tw_entries(p.nfft)) * sizeof(cx<float>)
+template <int FPT, typename FFT, bool LEAN>
+int herm_launch_as(W2Params& p, cudaStream_t st) {
+    const int fnn = p.nfft / 2 + 1;
+    const size_t f32 = (((size_t)4 * p.nfft + (FFT::kRegTw ? 0 : FFT::tw_entries(p.nfft))) * sizeof(cx<float>) + 15) & ~(size_t)15;
+    const size_t smem = LEAN ? f32 + (size_t)4 * fnn * sizeof(cd)
                              : (size_t)(4 * p.nfft + FFT::tw_entries(p.nfft)) * sizeof(cd) +
                                    (size_t)FFT::tw_entries(p.nfft) * sizeof(cx<float>);
     if (smem > 48 * 1024)
-        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
+    if (const char* e = getenv("SC_GRANGER_CARVEOUT"))  // experiment hook: shared-memory carveout in percent
+        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT, LEAN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        atoi(e)));
     int per_sm = 1;
-    SC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, granger_herm_kernel<FPT, FFT>, kThreads, smem));
+    SC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, granger_herm_kernel<FPT, FFT, LEAN>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
     const long long nprob = p.B * p.n_pairs;
     long long grid = (long long)sc_num_sms() * per_sm;
-    if (grid > nprob) grid = nprob;
-    granger_herm_kernel<FPT, FFT><<<(unsigned)grid, kThreads, smem, st>>>(p);
+    const long long ngroups = (nprob + kGroup - 1) / kGroup;
+    if (grid > ngroups) grid = ngroups;
+    granger_herm_kernel<FPT, FFT, LEAN><<<(unsigned)grid, kThreads, smem, st>>>(p);
     SC_LAUNCH_OK();
     return SC_OK;
+}
+
+template <int FPT, typename FFT>
+int herm_launch(W2Params& p, cudaStream_t st) {
+    // mixed-precision mode (needs the fp32 twiddles) with a plan whose twiddles fit in registers -> the lean kernel
+    // (fp64 factor in shared memory, no twiddle tables); everything else -> the register kernel
+    // Measured (profiles/r02_granger_experiments.txt): the lean kernel runs config 4 in 305.5 ms, the register kernel
+    // in 302.6 ms -- the iteration is bound by the lock-step alternation of load / butterfly / store phases between
+    // barriers, not by shared-memory wavefronts, registers or the fp64 pipe -- so the simpler register kernel stays
+    // the default and the lean one is kept behind SC_GRANGER_LEAN=1 for the record.
+    const char* lean = getenv("SC_GRANGER_LEAN");
+    if (FFT::kRegTw && p.tw32 && p.mixed && lean && lean[0] == '1') return herm_launch_as<FPT, FFT, true>(p, st);
+    return herm_launch_as<FPT, FFT, false>(p, st);
 }
 
 }  // namespace

@@ -8,6 +8,10 @@
 // TS real series are packed two-per-complex-FFT, transformed by the CTA-cooperative Stockham
 // FFT (fft_device.cuh), unpacked to half (or full) spectra and stored with the signal axis
 // fastest, so the CSM stage reads [F][2][R][S] tiles directly.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include <type_traits>
 
 #include "fft_device.cuh"
@@ -17,6 +21,51 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWsCtas = 296;
+constexpr int kTmaBoxRows = 256;  // rows (samples) per TMA box: the hardware limit of a box dimension
+
+// ---- TMA (cp.async.bulk.tensor) staging of the n x TS input slab --------------------------------------------
+// The slab of one (window, trial, signal tile) is a 3-D box {TS signals, 1 trial, rows} of the (N, T, S) series.
+// One elected thread issues ceil(n / 256) bulk tensor copies that land densely ([row][TS]) in shared memory and
+// complete on an mbarrier: the load costs no registers and no issue slots of the other 255 threads, the signal
+// tail (S not a multiple of TS) and rows beyond the series are zero-filled by the hardware.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (spin > (1u << 28)) __trap();  // watchdog: a broken pipeline must not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// first radix / remaining stages of a compile-time plan (the first stage is fused with the taper product)
+template <typename PLAN> struct PlanHead;
+template <int N, int R0, int... REST> struct PlanHead<ScStaticPlan<N, R0, REST...>> {
+    static constexpr int n = N, r0 = R0;
+    template <int NB, typename SYNC>
+    static __device__ __forceinline__ cx<float>* rest(cx<float>* src, cx<float>* dst, const cx<float>* tws, int tid,
+                                                      int nthreads, SYNC sync) {
+        return ScStaticStages<float, N, R0, REST...>::template run<NB>(src, dst, tws, false, tid, nthreads, sync);
+    }
+};
 
 struct MtParams {
     const float* x;
@@ -52,10 +101,19 @@ __device__ __forceinline__ int tile_ix(int j, int s) {
     return j * TS + ((((s >> 1) ^ ((j >> SH) & (NP - 1))) << 1) | (s & 1));
 }
 
-template <int TS, bool WS, typename PLAN>
-__global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtParams p) {
+// slab element (sample j, series s): XOR-swizzled for the register-loaded tile, dense for the TMA-staged one (whose
+// fused first FFT stage reads whole 16-byte quarter rows, which is conflict-free without a swizzle)
+template <int TS, bool TMA>
+__device__ __forceinline__ int tile_at(int j, int s) {
+    return TMA ? j * TS + s : tile_ix<TS>(j, s);
+}
+
+template <int TS, bool WS, typename PLAN, bool TMA = false>
+__global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                      const MtParams p) {
     constexpr bool STATIC = !std::is_same<PLAN, DynPlan>::value;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    static_assert(!TMA || (STATIC && !WS && TS == 8), "the TMA path is the compile-time-plan, 8-series tile kernel");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NP = TS / 2;  // complex FFTs per taper
     const int n = p.n, nfft = p.nfft;
     const int ncopy = n < nfft ? n : nfft;
@@ -67,21 +125,44 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
     const cx<float>* tw;
     __shared__ double red[2][kThreads];
     __shared__ float trend_a[TS], trend_b[TS];
+    __shared__ __align__(8) uint64_t slab_bar;
+    uint32_t slab_parity = 0;
+    if (TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&slab_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
     if (WS) {
         bufA = p.ws + (size_t)blockIdx.x * 2 * NP * nfft;
         bufB = bufA + (size_t)NP * nfft;
         tw = p.tw;
     } else {
-        bufA = reinterpret_cast<cx<float>*>(smem_raw);
+        // TMA: the slab is the 128-byte aligned head of the buffer, padded to whole boxes
+        const int tile_rows = TMA ? ((n + kTmaBoxRows - 1) / kTmaBoxRows) * kTmaBoxRows : 0;
+        bufA = reinterpret_cast<cx<float>*>(smem_raw + (size_t)tile_rows * TS * 4);
         bufB = bufA + (size_t)NP * nfft;
         cx<float>* tws = bufB + (size_t)NP * nfft;
-        tile = reinterpret_cast<float*>(tws + nfft);
+        tile = TMA ? reinterpret_cast<float*>(smem_raw) : reinterpret_cast<float*>(tws + nfft);
         if constexpr (STATIC) ScStaticFft<float, PLAN>::fill(tws, p.tw, threadIdx.x, kThreads);
         else for (int q = threadIdx.x; q < nfft; q += kThreads) tws[q] = p.tw[q];
         tw = tws;
         __syncthreads();
     }
 
+    // one elected thread stages the slab of `it` with bulk tensor copies (see the TMA helpers above)
+    auto issue_slab = [&](long long it) {
+        if (threadIdx.x != 0) return;
+        const long long ti = it % tiles, tt = (it / tiles) % p.T, ww = p.w0 + it / (tiles * p.T);
+        const int nbox = (n + kTmaBoxRows - 1) / kTmaBoxRows;
+        // earlier generic-proxy accesses of the slab (ordered by the barrier before this call) must be visible to
+        // the async proxy before it overwrites the buffer
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&slab_bar, (uint32_t)(nbox * kTmaBoxRows * TS * 4));
+        for (int bx = 0; bx < nbox; ++bx)
+            tma_load_3d(tile + (size_t)bx * kTmaBoxRows * TS, &tmap, &slab_bar, (int)(ti * TS), (int)tt,
+                        (int)(ww * p.step) + bx * kTmaBoxRows);
+    };
     for (long long item = blockIdx.x; item < total; item += gridDim.x) {
         const long long tile_i = item % tiles;
         const long long t = (item / tiles) % p.T;
@@ -102,7 +183,19 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
         // exposed DRAM latency of the kernel)
         constexpr int LD = 8;
         int bad = 0;
-        for (int j0 = jr; j0 < n; j0 += LD * JSTEP) {
+        if (TMA) {
+            if (item == blockIdx.x) issue_slab(item);  // later slabs were prefetched under the previous item's last taper
+            mbar_wait(&slab_bar, slab_parity);
+            slab_parity ^= 1;
+            // detrend statistics + NaN/Inf scan from shared memory (8 lanes per row: conflict-free)
+            for (int j = jr; j < n; j += JSTEP) {
+                const float v = tile[j * TS + sl];
+                bad |= !isfinite(v);
+                sum += v;
+                if (p.detrend == SC_DETREND_LINEAR) sumu += ((j + 1.0) / n - ubar) * v;
+            }
+        }
+        for (int j0 = jr; j0 < n && !TMA; j0 += LD * JSTEP) {
             float v[LD];
 #pragma unroll
             for (int u = 0; u < LD; ++u) {
@@ -146,10 +239,10 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
             trend_b[threadIdx.x] = 0.f;
         }
         __syncthreads();
-        if (!WS && p.detrend != SC_DETREND_NONE) {
+        if (!WS && p.detrend != SC_DETREND_NONE && (!TMA || unpack)) {
             const float ta = trend_a[sl], tb = trend_b[sl];
             const float invn = 1.0f / n;
-            for (int j = jr; j < ncopy; j += JSTEP) tile[tile_ix<TS>(j, sl)] -= ta * ((j + 1) * invn) + tb;
+            for (int j = jr; j < ncopy; j += JSTEP) tile[tile_at<TS, TMA>(j, sl)] -= ta * ((j + 1) * invn) + tb;
             __syncthreads();
         }
 
@@ -175,11 +268,50 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
                                 v1 -= trend_a[sa + 1] * u + trend_b[sa + 1];
                             }
                         } else {
-                            v0 = tile[tile_ix<TS>(j, sa)];
+                            v0 = tile[tile_at<TS, TMA>(j, sa)];
                         }
                         z = cmake<float>(v0 * hv, v1 * hv);
                     }
                     bufA[(size_t)pp * nfft + j] = z;
+                }
+            } else if constexpr (TMA) {
+                // Taper product FUSED into the first FFT stage: butterfly j of the first stage needs the samples
+                // j + t*M (t < R0) of its sequence, so it reads them straight from the slab -- one 16-byte quarter
+                // row (4 series = 2 packed sequences) per sample, detrend and taper applied in registers -- and
+                // writes the stage output; the tapered sequences never exist in shared memory (one write + one
+                // read of NP*nfft complex values and one barrier less per taper).
+                constexpr int R0 = PlanHead<PLAN>::r0;
+                constexpr int M = PlanHead<PLAN>::n / R0;
+                const float invn = 1.0f / n;
+                for (int idx = threadIdx.x; idx < 2 * M; idx += kThreads) {
+                    const int hq = idx / M, j = idx - hq * M;  // quarter-row pair (series 4*hq .. 4*hq+3), butterfly
+                    const float ta0 = trend_a[4 * hq], ta1 = trend_a[4 * hq + 1], ta2 = trend_a[4 * hq + 2],
+                                ta3 = trend_a[4 * hq + 3];
+                    const float tb0 = trend_b[4 * hq], tb1 = trend_b[4 * hq + 1], tb2 = trend_b[4 * hq + 2],
+                                tb3 = trend_b[4 * hq + 3];
+                    cx<float> va[R0], vb[R0];
+#pragma unroll
+                    for (int tt = 0; tt < R0; ++tt) {
+                        const int row = j + tt * M;
+                        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float hv = 0.f;
+                        if (row < ncopy) {
+                            xv = *reinterpret_cast<const float4*>(tile + row * TS + 4 * hq);
+                            hv = __ldg(h + row);
+                        }
+                        const float u = (row + 1) * invn;
+                        va[tt] = cmake<float>((xv.x - (ta0 * u + tb0)) * hv, (xv.y - (ta1 * u + tb1)) * hv);
+                        vb[tt] = cmake<float>((xv.z - (ta2 * u + tb2)) * hv, (xv.w - (ta3 * u + tb3)) * hv);
+                    }
+                    sc_dft<float, R0>(va, false, (const cx<float>*)0, PlanHead<PLAN>::n);
+                    sc_dft<float, R0>(vb, false, (const cx<float>*)0, PlanHead<PLAN>::n);
+                    cx<float>* da = bufA + (size_t)(2 * hq) * nfft + j * R0;
+                    cx<float>* db = da + nfft;
+#pragma unroll
+                    for (int q = 0; q < R0; ++q) {
+                        da[q] = va[q];
+                        db[q] = vb[q];
+                    }
                 }
             } else {
                 // one thread per sample j: the taper value is loaded once and applied to all TS series
@@ -195,8 +327,13 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
                 }
             }
             __syncthreads();
+            if (TMA && !unpack && k == p.K - 1 && item + gridDim.x < total)
+                issue_slab(item + gridDim.x);  // the slab is dead after the last taper's first stage: prefetch the next
             const cx<float>* res;
-            if constexpr (STATIC)
+            if constexpr (TMA) {
+                if (unpack) res = ScStaticFft<float, PLAN>::template run<NP>(bufA, bufB, tw, false, threadIdx.x, kThreads, CtaSync());
+                else res = PlanHead<PLAN>::template rest<NP>(bufA, bufB, tw, threadIdx.x, kThreads, CtaSync());
+            } else if constexpr (STATIC)
                 res = ScStaticFft<float, PLAN>::template run<NP>(bufA, bufB, tw, false, threadIdx.x, kThreads, CtaSync());
             else
                 res = sc_cta_fft<float>(bufA, bufB, NP, nfft, p.plan, tw, false);
@@ -281,6 +418,7 @@ __global__ void __launch_bounds__(kThreads, WS ? 1 : 2) mt_fft_kernel(const MtPa
             __syncthreads();
           }
         }
+        if (TMA && unpack && item + gridDim.x < total) issue_slab(item + gridDim.x);  // unpacked slabs: no prefetch
     }
 }
 
@@ -298,14 +436,61 @@ int mt_pick_ts(int n, int nfft) {
     return 0;  // workspace mode
 }
 
-template <int TS, bool WS, typename PLAN = DynPlan>
-int mt_launch(const MtParams& p, size_t smem, long long grid, cudaStream_t st) {
+template <int TS, bool WS, typename PLAN = DynPlan, bool TMA = false>
+int mt_launch(const MtParams& p, size_t smem, long long grid, cudaStream_t st, const CUtensorMap* tmap = nullptr) {
     if (smem > 48 * 1024)
-        SC_CUDA_OK(cudaFuncSetAttribute(mt_fft_kernel<TS, WS, PLAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SC_CUDA_OK(cudaFuncSetAttribute(mt_fft_kernel<TS, WS, PLAN, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
-    mt_fft_kernel<TS, WS, PLAN><<<(unsigned)grid, kThreads, smem, st>>>(p);
+    CUtensorMap none;
+    if (!tmap) {
+        memset(&none, 0, sizeof(none));
+        tmap = &none;
+    }
+    mt_fft_kernel<TS, WS, PLAN, TMA><<<(unsigned)grid, kThreads, smem, st>>>(*tmap, p);
     SC_LAUNCH_OK();
     return SC_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn mt_get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (tried) return fn;
+    tried = true;
+    const char* off = getenv("SC_B200_DISABLE_TMA_FFT");
+    if (off && off[0] == '1') return nullptr;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+    return fn;
+}
+
+// tensor map of the series x (N, T, S) float32 with box {8 signals, 1 trial, 256 samples}; false when the series
+// does not meet the TMA constraints (16-byte aligned base and row strides)
+bool mt_make_tmap(const MtParams& p, CUtensorMap* tmap) {
+    EncodeTiledFn enc = mt_get_encode();
+    if (!enc || (p.S & 3) != 0 || (reinterpret_cast<uintptr_t>(p.x) & 15) != 0) return false;
+    if (p.S >= (1LL << 31) || p.T >= (1LL << 31) || p.N >= (1LL << 31)) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)p.S, (cuuint64_t)p.T, (cuuint64_t)p.N};
+    const cuuint64_t gstr[2] = {(cuuint64_t)p.S * 4, (cuuint64_t)p.T * p.S * 4};  // bytes, dims 1..2
+    const cuuint32_t box[3] = {8, 1, (cuuint32_t)kTmaBoxRows};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p.x), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t mt_smem_bytes_tma(int n, int nfft) {
+    const size_t rows = (size_t)((n + kTmaBoxRows - 1) / kTmaBoxRows) * kTmaBoxRows;
+    return rows * 8 * 4 + (size_t)2 * 4 * nfft * 8 + (size_t)nfft * 8;
 }
 
 __global__ void repack_kernel(const float2* __restrict__ coef, long long W, long long T, long long K, long long nfft,
@@ -424,6 +609,14 @@ extern "C" int sc_mt_fft(const float* x, int64_t N, int64_t T, int64_t S, const 
     const size_t smem = mt_smem_bytes(ts, n, nfft);
     const long long maxgrid = 1LL << 30;
     const long long grid = total < maxgrid ? total : maxgrid;
+    if (ts == 8 && (nfft == 1000 || nfft == 120)) {
+        CUtensorMap tmap;
+        const size_t smem_tma = mt_smem_bytes_tma(n, nfft);
+        if (smem_tma <= ((size_t)sc_max_smem_optin() - 20 * 1024) / 2 && mt_make_tmap(p, &tmap)) {
+            if (nfft == 1000) return mt_launch<8, false, ScPlan1000, true>(p, smem_tma, grid, st, &tmap);
+            return mt_launch<8, false, ScPlan120, true>(p, smem_tma, grid, st, &tmap);
+        }
+    }
     if (ts == 8 && nfft == 1000) return mt_launch<8, false, ScPlan1000>(p, smem, grid, st);
     if (ts == 8 && nfft == 120) return mt_launch<8, false, ScPlan120>(p, smem, grid, st);
     switch (ts) {

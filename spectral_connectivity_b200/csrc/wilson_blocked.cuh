@@ -391,7 +391,9 @@ __global__ void __launch_bounds__(256) zb_unscramble_kernel(const cd* Msrc, cd* 
 }
 
 // dst = src + lambda I  (src c128 or, with src_real, f64 promoted to c128)
-__global__ void zb_shift_copy_kernel(const cd* src, const double* src_real, double lam, long long count, int S, cd* dst) {
+__global__ void zb_shift_copy_kernel(const cd* src, const double* src_real, double lam_host, const double* lam_dev,
+                                     long long count, int S, cd* dst) {
+    const double lam = lam_dev ? lam_dev[0] : lam_host;
     const long long n = count * S * S;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const int rc = (int)(e % ((long long)S * S));

@@ -314,8 +314,9 @@ __global__ void mvar_lag0_kernel(const cd* g, long long B, int F, int nfft, int 
 }
 
 // per window: Minv = (H0 + lam I)^-1, Sigma = H0 H0^T; per kept frequency: H = G Minv  (:1705-1709, :1739-1748)
-__global__ void mvar_transfer_kernel(const cd* g, const double* h0, double lam, int F, int nfo, int S, cd* h_out,
-                                     double* sigma) {
+__global__ void mvar_transfer_kernel(const cd* g, const double* h0, double lam_host, const double* lam_dev, int F, int nfo,
+                                     int S, cd* h_out, double* sigma) {
+    const double lam = lam_dev ? lam_dev[0] : lam_host;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int SS = S * S;
     cd* aug = reinterpret_cast<cd*>(smem_raw);  // S x 2S
@@ -348,7 +349,8 @@ __global__ void mvar_transfer_kernel(const cd* g, const double* h0, double lam, 
 }
 
 // A = (H + lam I)^-1 per (window, frequency)  (connectivity.py:580-588)
-__global__ void mvar_inverse_kernel(const cd* h, double lam, long long BF, int S, cd* a_out) {
+__global__ void mvar_inverse_kernel(const cd* h, double lam_host, const double* lam_dev, long long BF, int S, cd* a_out) {
+    const double lam = lam_dev ? lam_dev[0] : lam_host;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int SS = S * S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -617,9 +619,9 @@ extern "C" int sc_mvar_lag0(const void* g_c128, int64_t B, int F, int nfft, int 
     return SC_OK;
 }
 
-extern "C" int sc_mvar_transfer(const void* g_c128, const double* h0, double lambda, int64_t B, int F, int n_freq_out,
-                                int S, void* out_h_c128, double* out_sigma, void* workspace, int64_t workspace_bytes,
-                                void* stream) {
+extern "C" int sc_mvar_transfer(const void* g_c128, const double* h0, double lambda, const double* lambda_device,
+                                int64_t B, int F, int n_freq_out, int S, void* out_h_c128, double* out_sigma,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
     SC_CHECK_ARG(g_c128 && h0 && out_h_c128 && B > 0 && F > 0 && n_freq_out > 0 && n_freq_out <= F,
                  "sc_mvar_transfer: bad argument");
     if (int rc = check_s(S, "sc_mvar_transfer")) return rc;
@@ -635,7 +637,7 @@ extern "C" int sc_mvar_transfer(const void* g_c128, const double* h0, double lam
         cd* work = reinterpret_cast<cd*>(workspace);
         cd* minv = work + (size_t)B * SS;
         unsigned char* scratch = reinterpret_cast<unsigned char*>(minv + (size_t)B * SS);
-        zb_shift_copy_kernel<<<grid_for(B * SS, 256), 256, 0, st>>>(nullptr, h0, lambda, B, S, work);
+        zb_shift_copy_kernel<<<grid_for(B * SS, 256), 256, 0, st>>>(nullptr, h0, lambda, lambda_device, B, S, work);
         if (int rc = zb_inverse(work, minv, B, S, nullptr, 1, nullptr, scratch, st)) return rc;
         ZGemmParams g;
         g.A = reinterpret_cast<const cd*>(g_c128); g.Bm = minv; g.C = reinterpret_cast<cd*>(out_h_c128);
@@ -648,14 +650,14 @@ extern "C" int sc_mvar_transfer(const void* g_c128, const double* h0, double lam
         return SC_OK;
     }
     const size_t smem = (size_t)(2 * S * S + S) * sizeof(cd);
-    mvar_transfer_kernel<<<(unsigned)B, 256, smem, st>>>(reinterpret_cast<const cd*>(g_c128), h0, lambda, F, n_freq_out, S,
-                                                          reinterpret_cast<cd*>(out_h_c128), out_sigma);
+    mvar_transfer_kernel<<<(unsigned)B, 256, smem, st>>>(reinterpret_cast<const cd*>(g_c128), h0, lambda, lambda_device, F,
+                                                          n_freq_out, S, reinterpret_cast<cd*>(out_h_c128), out_sigma);
     SC_LAUNCH_OK();
     return SC_OK;
 }
 
-extern "C" int sc_mvar_inverse(const void* h_c128, double lambda, int64_t BF, int S, void* out_a_c128, void* workspace,
-                               int64_t workspace_bytes, void* stream) {
+extern "C" int sc_mvar_inverse(const void* h_c128, double lambda, const double* lambda_device, int64_t BF, int S,
+                               void* out_a_c128, void* workspace, int64_t workspace_bytes, void* stream) {
     SC_CHECK_ARG(h_c128 && out_a_c128 && BF > 0, "sc_mvar_inverse: bad argument");
     if (int rc = check_s(S, "sc_mvar_inverse")) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -669,7 +671,7 @@ extern "C" int sc_mvar_inverse(const void* h_c128, double lambda, int64_t BF, in
         cd* work = reinterpret_cast<cd*>(workspace);
         unsigned char* scratch = reinterpret_cast<unsigned char*>(work + (size_t)BF * S * S);
         zb_shift_copy_kernel<<<grid_for(BF * (long long)S * S, 256), 256, 0, st>>>(reinterpret_cast<const cd*>(h_c128), nullptr,
-                                                                                  lambda, BF, S, work);
+                                                                                  lambda, lambda_device, BF, S, work);
         return zb_inverse(work, reinterpret_cast<cd*>(out_a_c128), BF, S, nullptr, 1, nullptr, scratch, st);
     }
     const size_t per_warp = (size_t)(2 * S * S + S) * sizeof(cd);
@@ -678,7 +680,7 @@ extern "C" int sc_mvar_inverse(const void* h_c128, double lambda, int64_t BF, in
     if (per_warp * wpb > 48 * 1024)
         SC_CUDA_OK(cudaFuncSetAttribute(mvar_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)));
     mvar_inverse_kernel<<<(unsigned)((BF + wpb - 1) / wpb), wpb * 32, per_warp * wpb, st>>>(
-        reinterpret_cast<const cd*>(h_c128), lambda, BF, S, reinterpret_cast<cd*>(out_a_c128));
+        reinterpret_cast<const cd*>(h_c128), lambda, lambda_device, BF, S, reinterpret_cast<cd*>(out_a_c128));
     SC_LAUNCH_OK();
     return SC_OK;
 }

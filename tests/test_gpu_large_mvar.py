@@ -38,11 +38,11 @@ def test_blocked_inverse_vs_numpy(sc, s):
     wsb = lib.sc_mvar_workspace_bytes(n, 1, s)
     assert wsb > 0
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
-    L.check(lib.sc_mvar_inverse(L.ptr(ht), lam, n, s, L.ptr(out), L.ptr(ws), wsb, L.stream_ptr()), "sc_mvar_inverse")
+    L.check(lib.sc_mvar_inverse(L.ptr(ht), lam, None, n, s, L.ptr(out), L.ptr(ws), wsb, L.stream_ptr()), "sc_mvar_inverse")
     ref = np.linalg.inv(h + lam * np.eye(s))
     assert_parity(out.cpu().numpy(), ref, 1e-10, f"blocked inverse S={s}")
     # too small a workspace is refused, not overrun
-    rc = lib.sc_mvar_inverse(L.ptr(ht), lam, n, s, L.ptr(out), L.ptr(ws), 16, L.stream_ptr())
+    rc = lib.sc_mvar_inverse(L.ptr(ht), lam, None, n, s, L.ptr(out), L.ptr(ws), 16, L.stream_ptr())
     assert rc == -3
 
 
@@ -59,7 +59,7 @@ def test_blocked_transfer_vs_numpy(sc, s, nfo):
     sig = torch.empty((nb, s, s), dtype=torch.float64, device="cuda")
     wsb = lib.sc_mvar_workspace_bytes(nb, 2, s)
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
-    L.check(lib.sc_mvar_transfer(L.ptr(gt), L.ptr(h0t), lam, nb, nf, nfo, s, L.ptr(h), L.ptr(sig), L.ptr(ws), wsb,
+    L.check(lib.sc_mvar_transfer(L.ptr(gt), L.ptr(h0t), lam, None, nb, nf, nfo, s, L.ptr(h), L.ptr(sig), L.ptr(ws), wsb,
                                  L.stream_ptr()), "sc_mvar_transfer")
     ref = g[:, :nfo] @ np.linalg.inv(h0 + lam * np.eye(s))[:, None]
     assert_parity(h.cpu().numpy(), ref, 1e-10, "H = G (H0 + lam I)^-1")
