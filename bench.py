@@ -511,13 +511,16 @@ def run_gpu(args, wl_name, wl, shard, ctx):
         return run_measures(cc, out=bufs)
 
     try:
+        if args.no_e2e:
+            raise RuntimeError("end-to-end part skipped (--no-e2e)")
         # persistent page-locked result buffers, as a pipeline calling compute() repeatedly would hold them
         # (compute(out=...)): nothing is allocated or page-locked inside the timed region
         fused = [name for name in measures if name in sc.connectivity.MEASURES]
+        probe = step_e2e()
+        d2h = int(sum(v.nbytes for v in probe.values()))
         if fused:
-            probe = step_e2e()
             bufs = {name: sc.pinned_empty(probe[name].shape, probe[name].dtype) for name in fused}
-            del probe
+        del probe
         for _ in range(max(args.e2e_warmup - 1, 0)):  # untimed: staging buffers and allocator reach steady state
             res = step_e2e()
             d2h = int(sum(v.nbytes for v in res.values()))
@@ -541,7 +544,7 @@ def run_gpu(args, wl_name, wl, shard, ctx):
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
         e2e_value = units_total / (e2e_ms * 1e-3)
     # ---- the host link all ranks share: pinned H2D + D2H copies issued by every rank at the same time ----------
-    def host_link_gbs(nbytes=1 << 28, reps=4):
+    def host_link_gbs(nbytes=1 << 30, reps=3):
         hs, hd = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True), torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         ds, dd = torch.empty(nbytes, dtype=torch.uint8, device=dev), torch.empty(nbytes, dtype=torch.uint8, device=dev)
         s_in, s_out = _lib.side_stream(dev, "h2d"), _lib.side_stream(dev, "d2h")
@@ -590,10 +593,12 @@ def run_gpu(args, wl_name, wl, shard, ctx):
         # power: a full pass over the coefficients, or -- when the CSM is computed anyway -- its real diagonal
         "power": ("hbm", (12.0 * wown * fnn * S if ("csm" in stages or has_granger) else
                           8.0 * wloc * tk * fnn * S + 4.0 * wloc * fnn * S)),
-        # tensor stage: TF32 flops actually issued = upper-triangular 128x128 tiles x 12 MMAs (Re/Im x
-        # (hi*hi + hi*lo + lo*hi) x 2 products) x 2*128*128*8 per 8 observations
-        "csm": ("tensor", wloc * fnn * (math.ceil(S / 128) * (math.ceil(S / 128) + 1) // 2) * math.ceil(tk / 16) * 2
-                * 12 * 2.0 * 128 * 128 * 8),
+        # tensor stage (S >= 96, S % 32 == 0): TF32 flops actually issued = upper-triangular 128x128 tiles x 12 MMAs
+        # (Re/Im x (hi*hi + hi*lo + lo*hi) x 2 products) x 2*128*128*8 per 8 observations; smaller S: the SIMT kernel,
+        # 8 flops per observation and upper-triangle-tile pair
+        "csm": (("tensor", wloc * fnn * (math.ceil(S / 128) * (math.ceil(S / 128) + 1) // 2) * math.ceil(tk / 16) * 2
+                 * 12 * 2.0 * 128 * 128 * 8) if (S >= 96 and S % 32 == 0) else
+                ("fp32", 8.0 * wloc * fnn * tk * S * (S + 64) / 2)),
         "epilogue": ("hbm", 12.0 * wown * fnn * S * S),
         # fp32 SIMT: per observation and UPPER-TRIANGLE pair (the kernel mirrors) Im(x_i conj x_j) = 3 flops,
         # sign / |.| / square / three sums = 6 flops (PLI family, one pass for all four sums); PLV: the complex
@@ -683,11 +688,11 @@ def run_gpu(args, wl_name, wl, shard, ctx):
                 "host_buffers": "pinned input; results into persistent pinned buffers (compute(out=...))",
                 "cpu_affinity_rank0": cpus,
                 "host_link_gbs_all_ranks": link_gbs,
-                "host_link_floor_ms": ((h2d_total + d2h_total) / (link_gbs * 1e9) * 2 * 1e3 *
-                                       max(h2d_total, d2h_total) / (h2d_total + d2h_total) if link_gbs else None),
-                "host_link_note": "pinned H2D + D2H copies issued by every rank at once (256 MiB x 4 per direction), "
-                                  "aggregate GB/s over both directions; floor = the larger direction's bytes at half "
-                                  "that rate: what the end-to-end step cannot beat on this host whatever the GPUs do",
+                "host_link_ms_for_step_bytes": ((h2d_total + d2h_total) / (link_gbs * 1e9) * 1e3 if link_gbs else None),
+                "host_link_note": "pinned H2D + D2H copies issued by every rank at once (1 GiB x 3 per direction), "
+                                  "aggregate GB/s over both directions; host_link_ms_for_step_bytes = this step's "
+                                  "H2D + D2H bytes at that rate: the share of the end-to-end step that is the host "
+                                  "link, whatever the GPUs do",
                 **({} if e2e_ok else {"error": e2e_error or "another rank failed to stage its host buffers"})},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stages": stage_rows, "sanity": sanity,
         "simt_peaks_tflops": simt,
@@ -717,6 +722,7 @@ def main():
     ap.add_argument("--e2e-warmup", type=int, default=5)
     ap.add_argument("--replay-channels", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end part")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -269,7 +269,9 @@ class Connectivity:
         # Sized for all nfft bins whatever ``n_freq`` is streamed, so that the window ownership under
         # reduce_scatter is one fixed property of the object (``owned_windows``), not of the measure.
         per_window = max(gs.per_window_bin_bytes * nfft, nfft * n_sig * n_sig * 8)
-        return plan_window_chunks(n_win, per_window, min(self._max_chunk_bytes, 2 << 30), world=gs.world,
+        # up to 8 GiB per collective: with reduce_scatter a rank keeps 1/world of a chunk, and the full-matrix
+        # Wilson factorisation downstream wants several windows per batch (BASELINE config 5: 252 MB per window)
+        return plan_window_chunks(n_win, per_window, max(self._max_chunk_bytes, 8 << 30), world=gs.world,
                                   multiple_of_world=self._scatter(et))
 
     def _owned(self, n_freq, expectation_type=None):
