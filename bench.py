@@ -96,8 +96,9 @@ def workload_config(wl_name, wl, n_gpus, scaling="strong", shard="windows"):
                "no collective on the data path)")
     else:
         par = (f"strong: ONE recording, trials sharded {wl['T']}/{n_gpus} per GPU; partial cross-spectral sums "
-               "reduce-scattered along the window axis (NCCL, chunked, overlapped with the next chunk's FFT+CSM), "
-               "epilogues + Wilson window-sharded")
+               "reduce-scattered along the window axis (chunked, on a side stream under the next chunk's FFT+CSM: "
+               "NCCL, or with --reduce-impl p2p one fused pull-reduce + power + coherence kernel over NVLink peer "
+               "memory), Wilson window-sharded")
     return {"workload": f"BASELINE.json configs[{digit - 1}] (SURVEY.md config {digit})"
                         f"{' (reduced windows)' if len(wl_name) > 4 else ''}: {wl['S']}-channel x {wl['T']}-trial x "
                         f"{wl['N'] / wl['fs']:g} s @ {wl['fs']:.0f} Hz, {int(2 * wl['NW'] - 1)} tapers, "
@@ -418,7 +419,7 @@ def run_gpu(args, wl_name, wl, shard, ctx):
         x_dev = make_recording(wl, rank, dev)
     units_total = pair_freqs(wl) * (1 if strong else world)
     group = dist.group.WORLD if by_trials else None
-    ckw = dict(reduce_group=group, reduce_mode="reduce_scatter") if by_trials else {}
+    ckw = dict(reduce_group=group, reduce_mode="reduce_scatter", reduce_impl=args.reduce_impl) if by_trials else {}
 
     def build(x, output):
         m = sc.Multitaper(x, **kw)
@@ -719,6 +720,8 @@ def main():
                     help="N > 1, strong scaling: 'windows' (no collective), 'trials' (reduce_scatter of the partial "
                          "cross-spectral sums); 'auto' = the headline line is window-sharded and the same run also "
                          "measures the trial-sharded mode, reported under 'trial_sharded'")
+    ap.add_argument("--reduce-impl", default="p2p", choices=["nccl", "p2p"],
+                    help="--shard trials: NCCL reduce_scatter, or the fused peer-memory reduce + epilogue kernel")
     ap.add_argument("--e2e-warmup", type=int, default=5)
     ap.add_argument("--replay-channels", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -740,6 +743,7 @@ def main():
             if rank == 0:
                 line["trial_sharded"] = {k: second[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches")}
                 line["trial_sharded"]["parallelism"] = second["config"]["parallelism"]
+                line["trial_sharded"]["reduce_impl"] = args.reduce_impl
                 line["trial_sharded"]["stages"] = {k: {"ms_per_step": v["ms_per_step"], "frac": v.get("frac")}
                                                   for k, v in second["stages"].items()}
         if rank == 0:

@@ -243,6 +243,21 @@ int64_t sc_global_coherence_workspace_bytes(int64_t BF, int S);
  * (value f32 [BF], vector c64 [BF][S]), so that the next call on the same buffer yields the next eigenpair. */
 int sc_hermitian_deflate(void* csm_c64, int64_t BF, int S, const float* value, const void* vector_c64, void* stream);
 
+/* Trial-sharded mode (partition B): fused reduce-scatter + epilogue over NVLink peer memory.
+ * Every rank holds partial expectation sums in a buffer its peers can address (e.g. torch symmetric memory);
+ * ``peers`` is a HOST array of ``world`` device pointers, rank order, one per rank's buffer.  The caller orders
+ * "all ranks have written" before the launch and "all ranks have read" before a buffer is rewritten (device-side
+ * barrier of the symmetric-memory handle on the same stream).
+ *  sc_peer_reduce_csm  buffers hold c64 matrices [..][S][S]; matrices mat0 .. mat0+n_mat-1 are summed over the peers
+ *                      in rank order (deterministic) into out_csm (c64 [n_mat][S][S], may be NULL); out_power (f32
+ *                      [n_mat][S], may be NULL) receives the real diagonal (connectivity.py:441-445); measure = -1 or
+ *                      SC_M_COHERENCY .. SC_M_IMAG_COHERENCE writes that epilogue (connectivity.py:632-743) into
+ *                      out_measure in the same pass.  S must be even.
+ *  sc_peer_reduce      plain sum of n_bytes (multiple of 16) of float32 data at offset_bytes of every peer buffer. */
+int sc_peer_reduce_csm(const void* const* peers, int world, int64_t mat0, int64_t n_mat, int S, void* out_csm_c64,
+                       float* out_power, int measure, void* out_measure, void* stream);
+int sc_peer_reduce(const void* const* peers, int world, int64_t offset_bytes, int64_t n_bytes, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,8 @@ SIGNATURES = {
     "sc_global_coherence": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int64, _P]),
     "sc_global_coherence_workspace_bytes": (c_int64, [c_int64, c_int]),
     "sc_hermitian_deflate": (c_int, [_P, c_int64, c_int, _P, _P, _P]),
+    "sc_peer_reduce_csm": (c_int, [_P, c_int, c_int64, c_int64, c_int, _P, _P, c_int, _P, _P]),
+    "sc_peer_reduce": (c_int, [_P, c_int, c_int64, c_int64, _P, _P]),
     "sc_mvar_measure": (c_int, [c_int, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
 }
 
@@ -141,7 +143,9 @@ def side_stream(device, kind):
     key = (torch.device(device).index, kind)
     st = _SIDE_STREAMS.get(key)
     if st is None:
-        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        # the collective stream gets the higher priority: its few CTAs must be placed before the persistent
+        # Wilson / Granger grid of the previous chunk fills every SM
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1 if kind == "comm" else 0)
     return st
 
 

@@ -50,6 +50,7 @@ _PAIRWISE = {
 # by O(tolerance) = 1e-8 absolute (tests/test_gpu_round2.py::test_granger_and_dtf_every_expectation_type, 1e-5 vs
 # the live reference).
 _GRANGER_OK = tuple(EXPECTATION_AXES)
+_SYMM_SLOTS = {}  # (group name, device) -> peer-mapped partial-sum buffers of reduce_impl="p2p"
 MEASURES = ("power", "expectation_cross_spectral_matrix", "_phase_locking_value",
             "pairwise_spectral_granger_prediction") + tuple(_PAIRWISE)
 
@@ -85,8 +86,8 @@ class Connectivity:
 
     def __init__(self, fourier_coefficients, expectation_type="trials_tapers", frequencies=None,
                  time=None, blocks=None, dtype=None, *, output="numpy",
-                 max_chunk_bytes=4 << 30, reduce_group=None, reduce_mode="all_reduce", share_csm=False,
-                 _multitaper=None):
+                 max_chunk_bytes=None, reduce_group=None, reduce_mode="all_reduce", reduce_impl="nccl",
+                 share_csm=False, _multitaper=None):
         src = getattr(fourier_coefficients, "_sc_source", None)
         if (_multitaper is None and src is not None and isinstance(fourier_coefficients, torch.Tensor)
                 and fourier_coefficients._version == src[1]):
@@ -109,6 +110,8 @@ class Connectivity:
             raise ValueError("output must be 'numpy' or 'torch'")
         if reduce_mode not in ("all_reduce", "reduce_scatter"):
             raise ValueError("reduce_mode must be 'all_reduce' or 'reduce_scatter'")
+        if reduce_impl not in ("nccl", "p2p"):
+            raise ValueError("reduce_impl must be 'nccl' or 'p2p'")
         if not torch.cuda.is_available():
             raise RuntimeError("spectral_connectivity_b200 needs a CUDA device; there is no CPU fallback.")
         self._device = torch.device("cuda", torch.cuda.current_device())
@@ -142,9 +145,19 @@ class Connectivity:
         self._dtype = dtype
         self._fp64_wilson = dtype is not None and np.dtype(dtype) == np.dtype(np.complex128)
         self._output = output
+        # streamed window chunk: 4 GiB of planar coefficients; under a reduce group 8 GiB of partial sums per
+        # collective (with reduce_scatter a rank keeps 1/world of a chunk, and the full-matrix Wilson factorisation
+        # downstream wants several windows per batch -- BASELINE config 5: 252 MB per window)
+        if max_chunk_bytes is None:
+            max_chunk_bytes = (8 << 30) if reduce_group is not None else (4 << 30)
         self._max_chunk_bytes = int(max_chunk_bytes)
         self._reduce_group = reduce_group
         self._reduce_mode = reduce_mode
+        # reduce_impl="p2p" (reduce_scatter mode, cross-spectral sums): instead of NCCL, one kernel per rank pulls the
+        # rows it owns from every peer's partial sums over NVLink (torch symmetric memory), adds them in rank order and
+        # fuses the power extraction and one coherence-family epilogue (csrc/peer_reduce.cu)
+        self._reduce_impl = reduce_impl
+        self._symm = None
         # share_csm: keep the expected cross-spectral matrix of the first measure that needs it (if it fits in
         # _CSM_CACHE_BYTES) so that later measures -- the MVAR family, canonical / global coherence, the phase slope
         # index, further compute() calls -- skip the FFT + CSM pass (the reference recomputes both per measure,
@@ -269,9 +282,7 @@ class Connectivity:
         # Sized for all nfft bins whatever ``n_freq`` is streamed, so that the window ownership under
         # reduce_scatter is one fixed property of the object (``owned_windows``), not of the measure.
         per_window = max(gs.per_window_bin_bytes * nfft, nfft * n_sig * n_sig * 8)
-        # up to 8 GiB per collective: with reduce_scatter a rank keeps 1/world of a chunk, and the full-matrix
-        # Wilson factorisation downstream wants several windows per batch (BASELINE config 5: 252 MB per window)
-        return plan_window_chunks(n_win, per_window, max(self._max_chunk_bytes, 8 << 30), world=gs.world,
+        return plan_window_chunks(n_win, per_window, self._max_chunk_bytes, world=gs.world,
                                   multiple_of_world=self._scatter(et))
 
     def _owned(self, n_freq, expectation_type=None):
@@ -304,7 +315,25 @@ class Connectivity:
             _lib.check(rc, "sc_repack_coefficients")
         return xp, nb, nr
 
-    def _reduced(self, n_freq, kinds, expectation_type=None, scale=None):
+    def _symmetric_slots(self, nbytes):
+        """Three peer-mapped buffers (torch symmetric memory over the reduce group) of at least ``nbytes`` each: the
+        partial cross-spectral sums of three consecutive chunks.  Triple buffering makes ONE device-side barrier per
+        chunk sufficient: a slot is rewritten by the CSM kernel of chunk c+3, which this rank only enqueues after it
+        has waited for its own reduce of chunk c+1, i.e. after barrier c+1, which every peer enters only after its
+        reduce of chunk c -- the last reader of the slot -- has finished."""
+        import torch.distributed._symmetric_memory as symm_mem
+        # allocation + rendezvous is a collective handshake (IPC handle exchange, ~100 ms): cached per process and
+        # group, grown when a larger chunk comes along (every rank sees the same sizes, so all ranks grow together)
+        key = (self._reduce_group.group_name, self._device.index)
+        slots = _SYMM_SLOTS.get(key)
+        if slots is None or slots["nbytes"] < nbytes:
+            bufs = [symm_mem.empty(int(nbytes), dtype=torch.uint8, device=self._device) for _ in range(3)]
+            handles = [symm_mem.rendezvous(b, self._reduce_group) for b in bufs]
+            slots = _SYMM_SLOTS[key] = dict(nbytes=int(nbytes), bufs=bufs, handles=handles, used=0)
+        self._symm = slots
+        return slots
+
+    def _reduced(self, n_freq, kinds, expectation_type=None, scale=None, fuse=None):
         """Stream window chunks and yield the expectation sums of each: dict(o0, o1, w0, w1, csm, power, plv, pli)
         -- tensors hold rows [o0, o1) of THIS rank's output batch axis (``kinds`` selects which are produced;
         "power" comes from the CSM diagonal when the CSM is produced anyway).
@@ -328,6 +357,18 @@ class Connectivity:
         comm = _lib.side_stream(dev, "comm") if reduce else None
         st = _lib.stream_ptr()
         kinds = set(kinds)
+        # fused peer-memory reduce: reduce_scatter of the cross-spectral sums only (the headline path), even S
+        p2p = (scatter and self._reduce_impl == "p2p" and kinds <= {"csm", "power"} and "csm" in kinds
+               and n_sig % 2 == 0)
+        symm = None
+        if p2p:
+            bounds_ = self._chunk_bounds(n_freq, et)
+            max_rows = max(scatter_ownership(w1 - w0, gs.world, gs.rank)[0] * gs.world for w0, w1 in bounds_)
+            bw_ = 1
+            for a in (1, 2):
+                if a not in EXPECTATION_AXES[et]:
+                    bw_ *= self._shape[a]
+            symm = self._symmetric_slots(max_rows * bw_ * n_freq * n_sig * n_sig * 8)
         cached = self._csm_cache.get((n_freq, et)) if kinds <= {"csm", "power"} and "csm" in kinds else None
         if cached is not None:      # share_csm: an earlier measure already produced these sums
             rows_per_item = max(1, (1 << 30) // max(n_freq * n_sig * n_sig * 8, 1))
@@ -362,7 +403,18 @@ class Connectivity:
                     (t[nb:] if lead is None else t[:, nb:]).zero_()
                 return t
             for kind in sums:
-                if kind == "csm":
+                if kind == "csm" and p2p:
+                    slot = symm["used"] % 3
+                    symm["used"] += 1
+                    nfl = rows * n_freq * n_sig * n_sig * 2
+                    t = torch.view_as_complex(symm["bufs"][slot].view(torch.float32)[:nfl].view(rows, n_freq, n_sig, n_sig, 2))
+                    if rows > nb:
+                        t[nb:].zero_()
+                    item["slot"] = slot
+                    with _lib.timed("csm"):
+                        _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(t), st),
+                                   "sc_csm")
+                elif kind == "csm":
                     t = alloc((n_freq, n_sig, n_sig), torch.complex64)
                     with _lib.timed("csm"):
                         _lib.check(lib.sc_csm(_lib.ptr(xp), nb, n_freq, nr, n_sig, scale, _lib.CSM_CROSS, _lib.ptr(t), st),
@@ -392,7 +444,36 @@ class Connectivity:
                 item[kind] = t
             return item
 
+        enq = dict(o=0)
+
+        def enqueue_peer_reduce(item):
+            """barrier (all partial sums of the chunk are written) + the fused pull-reduce kernel, on the side stream"""
+            import ctypes
+            q, lo, hi = scatter_ownership(item["w1"] - item["w0"], gs.world, gs.rank)
+            bw = item["bw"]
+            valid = (hi - lo) * bw
+            o0 = enq["o"]
+            enq["o"] = o0 + valid
+            csm_r = torch.empty((valid, n_freq, n_sig, n_sig), dtype=torch.complex64, device=dev)
+            power_r = torch.empty((valid, n_freq, n_sig), dtype=torch.float32, device=dev) if want_power else None
+            code, dest = (-1, None) if fuse is None else (fuse[0], fuse[1](o0, o0 + valid))
+            hdl = symm["handles"][item["slot"]]
+            ptrs = (ctypes.c_void_p * gs.world)(*[int(p_) for p_ in hdl.buffer_ptrs])
+            ev = torch.cuda.Event()
+            ev.record()
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm), _lib.timed("collective"):
+                hdl.barrier(channel=0)
+                _lib.check(lib.sc_peer_reduce_csm(ptrs, gs.world, lo * bw * n_freq, valid * n_freq, n_sig,
+                                                  _lib.ptr(csm_r), _lib.ptr(power_r), code, _lib.ptr(dest),
+                                                  _lib.stream_ptr()), "sc_peer_reduce_csm")
+                done = torch.cuda.Event()
+                done.record(comm)
+            item.update(done=done, csm=csm_r, power=power_r, p2p=True, fused=dest is not None, valid=valid, o0=o0)
+
         def enqueue_collective(item):
+            if p2p:
+                return enqueue_peer_reduce(item)
             ev = torch.cuda.Event()
             ev.record()
             comm.wait_event(ev)
@@ -425,6 +506,12 @@ class Connectivity:
         def finish(item):
             if "done" in item:
                 torch.cuda.current_stream().wait_event(item["done"])
+            if item.get("p2p"):     # reduced matrix, power (and the fused measure) came out of the peer-reduce kernel
+                q, lo, hi = scatter_ownership(item["w1"] - item["w0"], gs.world, gs.rank)
+                item["w0"], item["w1"] = item["w0"] + lo, item["w0"] + hi
+                item["o1"] = item["o0"] + item["valid"]
+                state["o"] = item["o1"]
+                return item
             nb, bw = item["nb"], item["bw"]
             if scatter:
                 q, lo, hi = scatter_ownership(item["w1"] - item["w0"], gs.world, gs.rank)
@@ -599,7 +686,15 @@ class Connectivity:
                 host[name][b0:b1].copy_(res[name][b0:b1, :fnn], non_blocking=True)
 
         st = _lib.stream_ptr()
-        for item in self._reduced(n_freq, needs):
+        # reduce_impl="p2p": the first coherence-family measure is produced by the peer-reduce kernel itself
+        fuse, fused_name = None, None
+        if self._reduce_impl == "p2p" and self._scatter() and n_freq == fnn:
+            for name in measures:
+                if name in _PAIRWISE and _PAIRWISE[name][0] == "csm":
+                    fused_name = name
+                    fuse = (_PAIRWISE[name][1], lambda o0, o1, _n=name: res[_n][o0:o1])
+                    break
+        for item in self._reduced(n_freq, needs, fuse=fuse):
             b0, b1 = item["o0"], item["o1"]
             nb = b1 - b0
             if nb == 0:
@@ -618,6 +713,9 @@ class Connectivity:
                 if name not in _PAIRWISE:
                     continue
                 src_kind, code, _ = _PAIRWISE[name]
+                if name == fused_name and item.get("fused"):
+                    offload(name, b0, b1)
+                    continue
                 src = {"csm": csm, "plv": plv, "pli": pli}[src_kind]
                 if src_kind == "pli" and not src.is_contiguous():
                     src = src.contiguous()

@@ -48,10 +48,11 @@ def main():
     full["directed_transfer_function"] = full_c.directed_transfer_function()
     full["phase_slope_index"] = full_c.phase_slope_index()
     ok = True
-    for mode in ("all_reduce", "reduce_scatter"):
+    for mode, impl in (("all_reduce", "nccl"), ("reduce_scatter", "nccl"), ("reduce_scatter", "p2p")):
         # max_chunk_bytes=1 -> one chunk per `world` windows: several collectives, the last chunk ragged
+        # impl "p2p": the fused pull-reduce + power + coherence kernel over NVLink peer memory instead of NCCL
         part = sc.Connectivity.from_multitaper(sc.Multitaper(x[:, trials], **kw), reduce_group=dist.group.WORLD,
-                                               reduce_mode=mode, max_chunk_bytes=1)
+                                               reduce_mode=mode, reduce_impl=impl, max_chunk_bytes=1)
         assert part.n_observations == n_trials * 5, part.n_observations
         got = part.compute(measures)
         got["canonical_coherence"] = part.canonical_coherence(labels)[0]
@@ -65,7 +66,7 @@ def main():
             assert sum(int(c.item()) for c in counts) == 5, counts       # every window owned exactly once
         for k, ref in full.items():
             good, err = close(got[k], ref[own], 2e-5 if k == "directed_transfer_function" else 2e-6)
-            print(f"[rank {rank}] {mode:14s} {k}: windows {list(own)} err {err:.2e} {'ok' if good else 'MISMATCH'}",
+            print(f"[rank {rank}] {mode:14s} {impl:4s} {k}: windows {list(own)} err {err:.2e} {'ok' if good else 'MISMATCH'}",
                   flush=True)
             ok = ok and good
     flag = torch.tensor([1 if ok else 0], device="cuda")
