@@ -469,8 +469,11 @@ __device__ __forceinline__ void herm_iteration_defect(const GACC gacc,
 // Measured dead end, kept out: an 85-register cap for 3 CTAs per SM (fp64 factor in shared memory, tables kept)
 // leaves the iterations at the same speed -- they are throughput, not latency bound -- while the 11 KB of L1 that
 // three 72 KB CTAs leave slow the strided cross-spectral gathers down by 2x (profiles/r02_granger_experiments.txt).
-template <int FPT, typename FFT, bool LEAN>
-__global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Params p) {
+// MIXED = the launcher knows the call is in mixed-precision mode: like LEAN only the fp32 ping-pong buffers and tables
+// are allocated (40 KB instead of 88 KB at nfft = 1000) and the plain fp64 iteration is compiled out, but the fp64
+// factor of the defect iterations stays in registers.
+template <int FPT, typename FFT, bool LEAN, bool MIXED = false>
+__global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(const W2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[6 * kWarps];
     __shared__ double tail_sh[3];
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
     // mixed-precision mode runs EVERY FFT in fp32 (fp32 phase + defect-correction iterations): the fp64 ping-pong
     // buffers and twiddle tables are then not allocated at all (40 KB instead of 88 KB of shared memory at
     // nfft = 1000, the rest stays L1 for the cross-spectral gathers)
-    constexpr bool lean = LEAN;
+    constexpr bool lean = LEAN || MIXED;  // fp32 buffers only
     cd* ZA = reinterpret_cast<cd*>(smem_raw);
     cd* ZB = ZA + 2 * (size_t)N;
     cd* tws = ZB + 2 * (size_t)N;
@@ -594,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
             int it0 = 0;
             // row scales D = diag(a00, a11)^-1/2 of the fp32 arithmetic (fp32 phase and defect iterations)
             const float r0 = (float)(1.0 / sqrt(a00)), r1 = (float)(1.0 / sqrt(a11));
-            if (p.tw32 && p.mixed) {
+            if (MIXED || (p.tw32 && p.mixed)) {
                 // ---- fp32 phase: the same iteration on the row-scaled problem S' = D S D, G' = D G with
                 // D = diag(a00, a11)^-1/2 (the iteration is equivariant under a left diagonal scaling, so
                 // this only keeps every intermediate O(1) in single precision).  It stops as soon as the
@@ -631,15 +634,15 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
             }
             for (int it = it0; it < p.max_iter && !converged; ++it) {
                 double st[6];
-                const bool defect = LEAN || (p.tw32 && p.mixed);
+                const bool defect = LEAN || MIXED || (p.tw32 && p.mixed);
                 if constexpr (LEAN) {
                     herm_iteration_defect<FPT, FFT, GSmem, kRT>(gsm, s00, s11, s01, r0, r1, ZAf, ZBf, p.plan, twsf, N, fnn,
                                                                 lag0f_sh, st, &twr);
                 } else {
-                    if (defect)
+                    if (MIXED || defect)
                         herm_iteration_defect<FPT, FFT>(greg, s00, s11, s01, r0, r1, ZAf, ZBf, p.plan, twsf, N, fnn,
                                                         lag0f_sh, st);
-                    else
+                    else if constexpr (!MIXED)
                         herm_iteration<double, FPT, FFT>(g00, g01, g10, g11, s00, s11, s01, 1.0, 1.0, 1.0, ZA, ZB, p.plan, tws,
                                                          N, fnn, lag0_sh, st);
                 }
@@ -784,27 +787,27 @@ __global__ void __launch_bounds__(kThreads, 2) granger_herm_kernel(const W2Param
 
 size_t herm_smem(int nfft) { return (size_t)5 * nfft * sizeof(cd) + (size_t)nfft * 8; }  // ZA, ZB, twiddles (f64 + f32)
 
-template <int FPT, typename FFT, bool LEAN>
+template <int FPT, typename FFT, bool LEAN, bool MIXED = false>
 int herm_launch_as(W2Params& p, cudaStream_t st) {
     const int fnn = p.nfft / 2 + 1;
-    const size_t f32 = (((size_t)4 * p.nfft + (FFT::kRegTw ? 0 : FFT::tw_entries(p.nfft))) * sizeof(cx<float>) + 15) & ~(size_t)15;
-    const size_t smem = LEAN ? f32 + (size_t)4 * fnn * sizeof(cd)
+    const size_t f32 = (((size_t)4 * p.nfft + (LEAN && FFT::kRegTw ? 0 : FFT::tw_entries(p.nfft))) * sizeof(cx<float>) + 15) & ~(size_t)15;
+    const size_t smem = MIXED ? f32 : LEAN ? f32 + (size_t)4 * fnn * sizeof(cd)
                              : (size_t)(4 * p.nfft + FFT::tw_entries(p.nfft)) * sizeof(cd) +
                                    (size_t)FFT::tw_entries(p.nfft) * sizeof(cx<float>);
     if (smem > 48 * 1024)
-        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT, LEAN, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
     if (const char* e = getenv("SC_GRANGER_CARVEOUT"))  // experiment hook: shared-memory carveout in percent
-        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT, LEAN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT, LEAN, MIXED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         atoi(e)));
     int per_sm = 1;
-    SC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, granger_herm_kernel<FPT, FFT, LEAN>, kThreads, smem));
+    SC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, granger_herm_kernel<FPT, FFT, LEAN, MIXED>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
     const long long nprob = p.B * p.n_pairs;
     long long grid = (long long)sc_num_sms() * per_sm;
     const long long ngroups = (nprob + kGroup - 1) / kGroup;
     if (grid > ngroups) grid = ngroups;
-    granger_herm_kernel<FPT, FFT, LEAN><<<(unsigned)grid, kThreads, smem, st>>>(p);
+    granger_herm_kernel<FPT, FFT, LEAN, MIXED><<<(unsigned)grid, kThreads, smem, st>>>(p);
     SC_LAUNCH_OK();
     return SC_OK;
 }
@@ -819,6 +822,7 @@ int herm_launch(W2Params& p, cudaStream_t st) {
     // the default and the lean one is kept behind SC_GRANGER_LEAN=1 for the record.
     const char* lean = getenv("SC_GRANGER_LEAN");
     if (FFT::kRegTw && p.tw32 && p.mixed && lean && lean[0] == '1') return herm_launch_as<FPT, FFT, true>(p, st);
+    if (p.tw32 && p.mixed) return herm_launch_as<FPT, FFT, false, true>(p, st);
     return herm_launch_as<FPT, FFT, false>(p, st);
 }
 
@@ -835,7 +839,7 @@ int sc_granger_herm_launch(scw::W2Params& p, void* stream) {
         return SC_ERR_UNSUPPORTED;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (p.nfft == 1000) return herm_launch<2, StatFft<ScPlan1000>>(p, st);
+    if (p.nfft == 1000) return herm_launch<(501 + scw::kThreads - 1) / scw::kThreads, StatFft<ScPlan1000>>(p, st);
     if (p.nfft == 120) return herm_launch<1, StatFft<ScPlan120>>(p, st);
     const int fpt = (p.nfft / 2 + 1 + scw::kThreads - 1) / scw::kThreads;
     switch (fpt) {

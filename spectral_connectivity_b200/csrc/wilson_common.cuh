@@ -6,7 +6,10 @@
 namespace scw {
 
 typedef cx<double> cd;
-constexpr int kThreads = 256;
+#ifndef SCW_THREADS
+#define SCW_THREADS 256  // threads per CTA of the Wilson / Granger kernels (one CTA = one problem)
+#endif
+constexpr int kThreads = SCW_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr double kEps64 = 2.220446049250313e-16;
 constexpr double kTikhonov = 1e-12;  // connectivity.py:79
