@@ -1082,11 +1082,6 @@ class Connectivity:
         """connectivity.py:1382-1426."""
         return self._mvar_measure(4)
 
-    # ---- rows still outside the device path (SURVEY.md section 8f rank 2 and "out of scope") ----
-    def _next_round(self, name):
-        raise NotImplementedError(
-            f"{name} is outside the current hot-path scope (SURVEY.md section 8f); see DESIGN.md")
-
     def _trials_tapers_csm(self, n_freq, private=False):
         """Expected CSM over trials x tapers per window (what the SVD-based measures are built on; they
         merge trials and tapers whatever ``expectation_type`` says, connectivity.py:1953-1976).  Rows = this rank's
@@ -1224,11 +1219,54 @@ class Connectivity:
             val, vec = val.flip(-1), vec.flip(-1)
         return self._finish(val.contiguous()), self._finish(vec.contiguous())
 
-    def group_delay(self, *args, **kwargs):
-        self._next_round("group_delay")
+    def _significant_band_phase(self, frequencies_of_interest, frequency_resolution, significance_threshold):
+        """Shared front half of ``delay`` / ``group_delay`` (connectivity.py:1466-1495, 1556-1578): band-passed
+        coherency of every signal pair (i < j), its unwrapped phase masked where the coherence is not significant.
+        The coherency comes from the device; the significance bookkeeping is host index work (_statistics.py)."""
+        from . import _statistics as stats
+        freqs = np.asarray(self.frequencies)
+        step = 1 if frequency_resolution is None else int(np.ceil(frequency_resolution / (freqs[1] - freqs[0])))
+        coh = self.coherency()
+        coh = coh.cpu().numpy() if isinstance(coh, torch.Tensor) else np.asarray(coh)
+        if frequencies_of_interest is not None:
+            band = (frequencies_of_interest[0] < freqs) & (freqs < frequencies_of_interest[1])
+            coh, freqs = np.take(coh, band.nonzero()[0], axis=-3), freqs[band]
+        n_sig = coh.shape[-1]
+        pairs = np.asarray(list(combinations(np.arange(n_sig), 2)))
+        coh = coh[..., pairs[:, 0], pairs[:, 1]].astype(np.complex128)
+        keep = stats.significant_frequencies(coh, self.n_observations, step,
+                                             significance_threshold=significance_threshold)
+        phase = np.ma.masked_array(np.unwrap(np.angle(coh), axis=-2), mask=~keep)
+        return phase, freqs, pairs, n_sig
 
-    def delay(self, *args, **kwargs):
-        self._next_round("delay")
+    def group_delay(self, frequencies_of_interest=None, frequency_resolution=None, significance_threshold=0.05):
+        """Average time delay of a broadband signal: slope of the significant coherence phase against frequency
+        (connectivity.py:1428-1528).  Returns (delay, slope, r_value), each (..., n_signals, n_signals)."""
+        from scipy.stats.mstats import linregress
+        phase, freqs, pairs, n_sig = self._significant_band_phase(frequencies_of_interest, frequency_resolution,
+                                                                  significance_threshold)
+        fit = np.ma.apply_along_axis(lambda y: linregress(freqs, y=y), -2, phase)
+        shape = (*phase.shape[:-2], n_sig, n_sig)
+        i, j = pairs[:, 0], pairs[:, 1]
+        slope = np.full(shape, np.nan)
+        slope[..., i, j] = np.asarray(fit[..., 0, :], dtype=float)
+        slope[..., j, i] = -1 * np.asarray(fit[..., 0, :], dtype=float)
+        r_value = np.ones(shape)
+        r_value[..., i, j] = np.asarray(fit[..., 2, :], dtype=float)
+        r_value[..., j, i] = np.asarray(fit[..., 2, :], dtype=float)
+        return slope / (2 * np.pi), slope, r_value
+
+    def delay(self, frequencies_of_interest=None, frequency_resolution=None, significance_threshold=0.05, n_range=3):
+        """Candidate delays (coherence phase + 2 pi k) / (2 pi), k = -n_range..n_range, of the significant
+        frequencies (connectivity.py:1530-1585).  Shape (..., n_frequencies, 2 n_range + 1, n_signals, n_signals)."""
+        phase, _, pairs, n_sig = self._significant_band_phase(frequencies_of_interest, frequency_resolution,
+                                                              significance_threshold)
+        turns = 2 * np.pi * np.arange(-n_range, n_range + 1)
+        cand = np.rollaxis((turns + phase[..., np.newaxis]) / (2 * np.pi), -1, -2)
+        out = np.full((*phase.shape[:-1], len(turns), n_sig, n_sig), np.nan)
+        out[..., pairs[:, 0], pairs[:, 1]] = cand
+        out[..., pairs[:, 1], pairs[:, 0]] = -cand
+        return out
 
     def phase_slope_index(self, frequencies_of_interest=None, frequency_resolution=None):
         """Weighted average of the coherency phase slope projected on the imaginary axis, shape

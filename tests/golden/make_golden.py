@@ -170,8 +170,43 @@ def round2_section(T, C):
         print(k, v.shape)
 
 
+def delay_section(T, C):
+    """delay / group_delay (connectivity.py:1428-1585) plus the statistics helpers they use
+    (statistics.py:21-59, 147-203).  Channel 1 is a 3-sample delayed copy of channel 0 plus noise, so the pair
+    is strongly coherent -- and the reference still finds nothing significant (n_obs2 = 0 default, see
+    spectral_connectivity_b200/_statistics.py): the fixtures record exactly that."""
+    import warnings
+    import spectral_connectivity.statistics as S
+    x = series(7, 600, 8, 4, 200.0)
+    x[3:, :, 1] += 0.8 * x[:-3, :, 0]
+    m = T.Multitaper(x, sampling_frequency=200.0, time_halfbandwidth_product=3, time_window_duration=1.0)
+    c = C.Connectivity.from_multitaper(m)
+    d = {"x": x, "meta": np.array([200.0, 3.0, 1.0])}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d["delay_band"] = np.asarray(c.delay(frequencies_of_interest=[5.0, 60.0]))
+        d["delay_res"] = np.asarray(c.delay(frequencies_of_interest=[5.0, 60.0], frequency_resolution=4.0, n_range=2))
+        for k, a in zip(("gd_delay", "gd_slope", "gd_r"), c.group_delay(frequencies_of_interest=[5.0, 60.0])):
+            d[k] = np.asarray(a)
+        rng = np.random.default_rng(3)
+        coh1 = 0.9 * rng.random((5, 40, 6)) * np.exp(2j * np.pi * rng.random((5, 40, 6)))
+        coh2 = 0.9 * rng.random((5, 40, 6)) * np.exp(2j * np.pi * rng.random((5, 40, 6)))
+        d["stat_coh1"], d["stat_coh2"] = coh1, coh2
+        d["stat_z_default"] = S.coherence_fisher_z_transform(coh1.copy(), 50)
+        d["stat_z_two"] = S.coherence_fisher_z_transform(coh1.copy(), 50, coh2.copy(), 70)
+        p = S.get_normal_distribution_p_values(d["stat_z_two"])
+        d["stat_p"] = p
+        d["stat_bh"] = S.Benjamini_Hochberg_procedure(p, alpha=0.2)
+        d["stat_bonf"] = S.Bonferroni_correction(p, alpha=0.2)
+        d["stat_groups"] = np.apply_along_axis(C._find_largest_independent_group, -2, p < 0.3, 2, 3)
+    np.savez_compressed(os.path.join(HERE, "delay.npz"), **d)
+
+
 def main():
     T, C, M = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "delay":
+        delay_section(T, C)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "round2":
         round2_section(T, C)
         return
@@ -319,6 +354,7 @@ def main():
     sv["global_vectors"] = np.asarray(gv_)[..., :1]
     np.savez_compressed(os.path.join(HERE, "svd_measures.npz"), **sv)
     psi_section(T, C)
+    delay_section(T, C)
     print("golden fixtures written to", HERE)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

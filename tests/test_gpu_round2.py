@@ -203,3 +203,23 @@ def test_multitaper_connectivity_wrapper_shares_one_pass(sc):
     assert np.asarray(one).shape == (1, 451)
     with pytest.raises(NotImplementedError):
         sc.multitaper_connectivity(x, 300.0, method="conditional_spectral_granger_prediction")
+
+
+def test_delay_and_group_delay_vs_live_reference(sc):
+    """delay / group_delay (connectivity.py:1428-1585) on the device coherency against the live
+    reference (tests/golden/delay.npz).  The reference's significance test never fires (its n_obs2 = 0 default turns
+    every z-score into NaN, see _statistics.py), so what is compared is its all-masked output, value for value."""
+    import warnings
+    g = golden("delay.npz")
+    fs, nw, dur = g["meta"]
+    c = sc.Connectivity.from_multitaper(sc.Multitaper(g["x"], sampling_frequency=fs, time_halfbandwidth_product=nw,
+                                                      time_window_duration=dur))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d1 = c.delay(frequencies_of_interest=[5.0, 60.0])
+        d2 = c.delay(frequencies_of_interest=[5.0, 60.0], frequency_resolution=4.0, n_range=2)
+        gd = c.group_delay(frequencies_of_interest=[5.0, 60.0])
+    for got, key in [(d1, "delay_band"), (d2, "delay_res"), (gd[0], "gd_delay"), (gd[1], "gd_slope"), (gd[2], "gd_r")]:
+        ref = g[key]
+        assert got.shape == ref.shape and np.array_equal(np.isnan(got), np.isnan(ref)), key
+        assert_parity(np.nan_to_num(got), np.nan_to_num(ref), TOL, key)

@@ -173,3 +173,51 @@ def test_bench_keeps_native_banners_off_stdout(tmp_path):
     assert res.returncode == 0, res.stderr
     assert res.stdout.strip() == '{"ok": 1}'
     assert "NATIVE BANNER" in res.stderr
+
+
+def test_statistics_helpers_match_reference():
+    """_statistics.py (host bookkeeping behind delay / group_delay) against the live reference's statistics.py and
+    connectivity.py:2102-2243 (tests/golden/make_golden.py: delay_section) -- float64 in, identical values out."""
+    from spectral_connectivity_b200 import _statistics as st
+    g = golden("delay.npz")
+    z_default = st.fisher_z(g["stat_coh1"].copy(), 50)
+    assert np.isnan(z_default).all() and np.isnan(g["stat_z_default"]).all()   # the reference's degenerate default
+    z = st.fisher_z(g["stat_coh1"].copy(), 50, g["stat_coh2"].copy(), 70)
+    assert_parity(z, g["stat_z_two"], 1e-12, "fisher z, two groups")
+    p = st.upper_tail_p(z)
+    assert_parity(p, g["stat_p"], 1e-12, "upper-tail p")
+    assert np.array_equal(st.benjamini_hochberg(g["stat_p"], alpha=0.2), g["stat_bh"])
+    assert np.array_equal(st.bonferroni(g["stat_p"], alpha=0.2), g["stat_bonf"])
+    assert np.array_equal(np.apply_along_axis(st._independent_run, -2, g["stat_p"] < 0.3, 2, 3), g["stat_groups"])
+    # statistics.py:43-47 (the reference's own documented example)
+    assert st.benjamini_hochberg(np.array([0.001, 0.02, 0.04, 0.3, 0.8])).tolist() == [True, True, False, False, False]
+
+
+def test_delay_group_delay_host_half_matches_reference():
+    """Host half of delay / group_delay (band-pass, significance mask, masked phase arithmetic) fed with the ORACLE's
+    coherency instead of the device's: equal to the live reference's outputs (tests/golden/delay.npz)."""
+    import types
+    from oracle import oracle as O
+    from spectral_connectivity_b200.connectivity import Connectivity
+    g = golden("delay.npz")
+    x = g["x"]
+    fs, nw, dur = g["meta"]
+    n, step, nfft = O.window_geometry(x.shape[0], fs, duration=dur)
+    coef = O.multitaper_fft(x, fs, O.dpss_tapers(n, nw, O.default_n_tapers(nw), fs), n, step, nfft)
+    fnn = nfft // 2 + 1
+    coh = O.coherency(coef)[..., :fnn, :, :]
+
+    class Host:
+        frequencies = O.frequencies(nfft, fs)[:fnn]
+        n_observations = O.n_observations(coef.shape, "trials_tapers")
+        coherency = staticmethod(lambda: coh.astype(np.complex64))
+    h = Host()
+    h._significant_band_phase = types.MethodType(Connectivity._significant_band_phase, h)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d1 = Connectivity.delay(h, frequencies_of_interest=[5.0, 60.0])
+        d2 = Connectivity.delay(h, frequencies_of_interest=[5.0, 60.0], frequency_resolution=4.0, n_range=2)
+        gd = Connectivity.group_delay(h, frequencies_of_interest=[5.0, 60.0])
+    for got, key in [(d1, "delay_band"), (d2, "delay_res"), (gd[0], "gd_delay"), (gd[1], "gd_slope"), (gd[2], "gd_r")]:
+        assert got.shape == g[key].shape and np.array_equal(np.isnan(got), np.isnan(g[key])), key
+        assert_parity(np.nan_to_num(got), np.nan_to_num(g[key]), 1e-5, key)
