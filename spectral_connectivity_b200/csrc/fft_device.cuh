@@ -102,21 +102,26 @@ template <typename R> SC_HD void sc_dft4(cx<R>* v, bool inv) {
 }
 
 template <typename R> SC_HD void sc_dft5(cx<R>* v, bool inv) {
+    // 32 real operations (12 additions + 20 fused multiply-adds): the sine products are folded into the output
+    // additions -- n1 = s1 (b1 + r b2), n2 = s1 (r b1 - b2) with r = s2/s1, and v1/v4 = m1 +- (-+i) n1 become one
+    // FMA per component instead of a multiply and an add.
     const R c1 = (R)0.30901699437494742410229341718282;   // cos(2pi/5)
     const R c2 = (R)-0.80901699437494742410229341718282;  // cos(4pi/5)
     const R s1 = (R)0.95105651629515357211643933337938;   // sin(2pi/5)
-    const R s2 = (R)0.58778525229247312916870595463907;   // sin(4pi/5)
+    const R rr = (R)0.61803398874989484820458683436564;   // sin(4pi/5) / sin(2pi/5)
+    const R sg = inv ? -s1 : s1;                          // forward: multiply by -i, inverse: by +i
     cx<R> a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
     cx<R> a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
     cx<R> m1 = cmake<R>(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
     cx<R> m2 = cmake<R>(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
-    cx<R> n1 = cmul_mi(cmake<R>(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y), inv);
-    cx<R> n2 = cmul_mi(cmake<R>(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y), inv);
+    cx<R> t1 = cmake<R>(b1.x + rr * b2.x, b1.y + rr * b2.y);
+    cx<R> t2 = cmake<R>(rr * b1.x - b2.x, rr * b1.y - b2.y);
     v[0] = cadd(v[0], cadd(a1, a2));
-    v[1] = cadd(m1, n1);
-    v[4] = csub(m1, n1);
-    v[2] = cadd(m2, n2);
-    v[3] = csub(m2, n2);
+    // -i s1 t = (s1 t.y, -s1 t.x) forward; +i s1 t = (-s1 t.y, s1 t.x) inverse
+    v[1] = cmake<R>(m1.x + sg * t1.y, m1.y - sg * t1.x);
+    v[4] = cmake<R>(m1.x - sg * t1.y, m1.y + sg * t1.x);
+    v[2] = cmake<R>(m2.x + sg * t2.y, m2.y - sg * t2.x);
+    v[3] = cmake<R>(m2.x - sg * t2.y, m2.y + sg * t2.x);
 }
 
 template <typename R> SC_HD void sc_dft8(cx<R>* v, bool inv) {
@@ -146,25 +151,19 @@ template <typename R> SC_HD void sc_dft8(cx<R>* v, bool inv) {
 }
 
 template <typename R> SC_HD void sc_dft10(cx<R>* v, bool inv) {
-    // decimation in frequency: 10 = 2 x 5; W10^a = exp(-2 pi i a/10)
-    const R wc[5] = {(R)1.0, (R)0.80901699437494742410229341718282, (R)0.30901699437494742410229341718282,
-                     (R)-0.30901699437494742410229341718282, (R)-0.80901699437494742410229341718282};
-    const R ws[5] = {(R)0.0, (R)0.58778525229247312916870595463907, (R)0.95105651629515357211643933337938,
-                     (R)0.95105651629515357211643933337938, (R)0.58778525229247312916870595463907};
+    // prime-factor (Good-Thomas) form of 10 = 2 x 5: with n = (5 n1 + 2 n2) mod 10 and k = (5 k1 + 6 k2) mod 10 the
+    // kernel W10^(n k) splits into W2^(n1 k1) W5^(n2 k2), so there are NO twiddle products between the radix-2 and
+    // the radix-5 parts (the decimation-in-frequency form needs four complex multiplications by W10^a).
     cx<R> e[5], o[5];
-#pragma unroll
-    for (int a = 0; a < 5; ++a) {
-        e[a] = cadd(v[a], v[a + 5]);
-        o[a] = csub(v[a], v[a + 5]);
-        if (a > 0) o[a] = cmul(o[a], cmake<R>(wc[a], inv ? ws[a] : -ws[a]));
-    }
+    e[0] = cadd(v[0], v[5]); o[0] = csub(v[0], v[5]);
+    e[1] = cadd(v[2], v[7]); o[1] = csub(v[2], v[7]);
+    e[2] = cadd(v[4], v[9]); o[2] = csub(v[4], v[9]);
+    e[3] = cadd(v[6], v[1]); o[3] = csub(v[6], v[1]);
+    e[4] = cadd(v[8], v[3]); o[4] = csub(v[8], v[3]);
     sc_dft5(e, inv);
     sc_dft5(o, inv);
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        v[2 * q] = e[q];
-        v[2 * q + 1] = o[q];
-    }
+    v[0] = e[0]; v[6] = e[1]; v[2] = e[2]; v[8] = e[3]; v[4] = e[4];
+    v[5] = o[0]; v[1] = o[1]; v[7] = o[2]; v[3] = o[3]; v[9] = o[4];
 }
 
 // O(r^2) register DFT for the odd primes 7, 11, 13; roots taken from the twiddle table.
@@ -315,23 +314,17 @@ SC_HD void sc_static_item(const cx<R>* src, cx<R>* dst, int j, const cx<R>* tws,
 template <typename R, int RADIX>
 SC_HD void sc_dft_lowhalf(cx<R>* v) {
     if (RADIX == 10) {
-        const R wc[5] = {(R)1.0, (R)0.80901699437494742410229341718282, (R)0.30901699437494742410229341718282,
-                         (R)-0.30901699437494742410229341718282, (R)-0.80901699437494742410229341718282};
-        const R ws[5] = {(R)0.0, (R)0.58778525229247312916870595463907, (R)0.95105651629515357211643933337938,
-                         (R)0.95105651629515357211643933337938, (R)0.58778525229247312916870595463907};
+        // prime-factor form (see sc_dft10) with v[5..9] = 0: the radix-2 part degenerates to sign changes
         cx<R> e[5], o[5];
-#pragma unroll
-        for (int a = 0; a < 5; ++a) {
-            e[a] = v[a];
-            o[a] = a > 0 ? cmul(v[a], cmake<R>(wc[a], -ws[a])) : v[a];
-        }
+        e[0] = v[0]; o[0] = v[0];
+        e[1] = v[2]; o[1] = v[2];
+        e[2] = v[4]; o[2] = v[4];
+        e[3] = v[1]; o[3] = cmake<R>(-v[1].x, -v[1].y);
+        e[4] = v[3]; o[4] = cmake<R>(-v[3].x, -v[3].y);
         sc_dft5(e, false);
         sc_dft5(o, false);
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            v[2 * q] = e[q];
-            v[2 * q + 1] = o[q];
-        }
+        v[0] = e[0]; v[6] = e[1]; v[2] = e[2]; v[8] = e[3]; v[4] = e[4];
+        v[5] = o[0]; v[1] = o[1]; v[7] = o[2]; v[3] = o[3]; v[9] = o[4];
     } else {
 #pragma unroll
         for (int t = RADIX / 2; t < RADIX; ++t) v[t] = cmake<R>((R)0, (R)0);
