@@ -130,7 +130,13 @@ template <> struct RealOps<double> {
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
 };
 template <> struct RealOps<float> {
-    static __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
+    // one MUFU.RCP (1 ulp) instead of the IEEE division sequence: the fp32 arithmetic only drives the iteration
+    // (the fixed point and the stopping test are decided in fp64), and |det|^2 is O(1) on the row-scaled problem
+    static __device__ __forceinline__ float rcp(float x) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
 };
 
 // log(total) - log(total - part) of connectivity.py:1773-1779 (0 -> eps in the denominator, non-positive
@@ -153,21 +159,22 @@ __device__ __forceinline__ float log_ratio(double total, double part) {
 // The plus operator (mpd.py:129-142) on the packed lag sequences z1 = c00 + i c11 (bb = 0) and
 // z2 = c01 + i c10 (bb = 1): scale by 1/N, halve lag 0, zero the lag-0 lower triangle (c10[0]); lags >= kcut
 // are zeroed by the caller.  Also records the lag-0 residual of G^-1 S G^-H - I.
+// The 1/N of the inverse transform is NOT applied here (it would cost two multiplies per kept lag): the sequences
+// stay scaled by N and the caller folds 1/N into the unpacking of the forward transforms.
 template <typename R> struct PlusWindow {
     R inv_n;
     R* lag0;
     __device__ __forceinline__ cx<R> operator()(int bb, int k, cx<R> z) const {
         if (k == 0) {
-            const R h = (R)0.5 * inv_n;
             if (bb == 0) {
                 lag0[0] = z.x * inv_n - (R)2;
                 lag0[2] = z.y * inv_n - (R)2;
-                return cmake<R>(z.x * h, z.y * h);
+                return cmake<R>(z.x * (R)0.5, z.y * (R)0.5);
             }
             lag0[1] = z.x * inv_n;
-            return cmake<R>(z.x * h, (R)0);
+            return cmake<R>(z.x * (R)0.5, (R)0);
         }
-        return cmake<R>(z.x * inv_n, z.y * inv_n);
+        return z;
     }
 };
 
@@ -245,40 +252,43 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
         Q = FFT::template run2<R>(o, c, plan, tw, false);
     }
     // ---- G <- G P (mpd.py:305-307) ----
+    // P = P0 + P' with the constant (lag-0) part P0 = I + (h00, h01; 0, h11): the non-constant part of the update,
+    // rest = G P', is formed directly (its maximum steers the precision hand-over and the tail entry), and
+    // G_new = G + dG with dG = G (P0 - I) + rest.  The transforms come back scaled by N (see PlusWindow): 0.5/N
+    // is folded into the Hermitian unpacking.
     R err2 = (R)0, rest2 = (R)0, c00 = (R)0, c10 = (R)0, c01m = (R)0, c11m = (R)0;
     const R h00 = (R)0.5 * lag0[0], h01 = (R)0.5 * lag0[1], h11 = (R)0.5 * lag0[2];  // P0 - I
+    const R h = (R)0.5 / (R)N;
+    const R o00 = (R)1 + h00, o11 = (R)1 + h11;
 #pragma unroll
     for (int q = 0; q < FPT; ++q) {
         const int f = threadIdx.x + q * kThreads;
         if (f < fnn) {
             const int fm = f == 0 ? 0 : N - f;
             const cx<R> a1 = Q[f], m1 = Q[fm], a2 = Q[N + f], m2 = Q[N + fm];
-            const R h = (R)0.5;
-            // Y1 = P00 + i P11, Y2 = P01 + i P10 (spectra of real sequences): even / odd Hermitian parts
-            const cx<R> p00 = cmake<R>(h * (a1.x + m1.x), h * (a1.y - m1.y));
-            const cx<R> p11 = cmake<R>(h * (a1.y + m1.y), h * (m1.x - a1.x));
-            const cx<R> p01 = cmake<R>(h * (a2.x + m2.x), h * (a2.y - m2.y));
+            // Y1 = P00 + i P11, Y2 = P01 + i P10 (spectra of real sequences): even / odd Hermitian parts, minus P0
+            const cx<R> p00 = cmake<R>(h * (a1.x + m1.x) - o00, h * (a1.y - m1.y));
+            const cx<R> p11 = cmake<R>(h * (a1.y + m1.y) - o11, h * (m1.x - a1.x));
+            const cx<R> p01 = cmake<R>(h * (a2.x + m2.x) - h01, h * (a2.y - m2.y));
             const cx<R> p10 = cmake<R>(h * (a2.y + m2.y), h * (m2.x - a2.x));
-            const cx<R> n00 = cadd(cmul(g00[q], p00), cmul(g01[q], p10));
-            const cx<R> n01 = cadd(cmul(g00[q], p01), cmul(g01[q], p11));
-            const cx<R> n10 = cadd(cmul(g10[q], p00), cmul(g11[q], p10));
-            const cx<R> n11 = cadd(cmul(g10[q], p01), cmul(g11[q], p11));
-            cx<R> dd;
-            dd = csub(n00, g00[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
-            dd.x -= h00 * g00[q].x; dd.y -= h00 * g00[q].y; rest2 = fmax(rest2, dd.x * dd.x + dd.y * dd.y);
-            dd = csub(n10, g10[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
-            dd.x -= h00 * g10[q].x; dd.y -= h00 * g10[q].y; rest2 = fmax(rest2, dd.x * dd.x + dd.y * dd.y);
-            dd = csub(n01, g01[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
-            dd.x -= h01 * g00[q].x + h11 * g01[q].x; dd.y -= h01 * g00[q].y + h11 * g01[q].y;
-            rest2 = fmax(rest2, dd.x * dd.x + dd.y * dd.y);
-            dd = csub(n11, g11[q]); err2 = fmax(err2, dd.x * dd.x + dd.y * dd.y);
-            dd.x -= h01 * g10[q].x + h11 * g11[q].x; dd.y -= h01 * g10[q].y + h11 * g11[q].y;
-            rest2 = fmax(rest2, dd.x * dd.x + dd.y * dd.y);
+            const cx<R> r00 = cadd(cmul(g00[q], p00), cmul(g01[q], p10));
+            const cx<R> r01 = cadd(cmul(g00[q], p01), cmul(g01[q], p11));
+            const cx<R> r10 = cadd(cmul(g10[q], p00), cmul(g11[q], p10));
+            const cx<R> r11 = cadd(cmul(g10[q], p01), cmul(g11[q], p11));
+            rest2 = fmax(rest2, fmax(fmax(r00.x * r00.x + r00.y * r00.y, r01.x * r01.x + r01.y * r01.y),
+                                     fmax(r10.x * r10.x + r10.y * r10.y, r11.x * r11.x + r11.y * r11.y)));
+            const cx<R> d00 = cmake<R>(r00.x + h00 * g00[q].x, r00.y + h00 * g00[q].y);
+            const cx<R> d10 = cmake<R>(r10.x + h00 * g10[q].x, r10.y + h00 * g10[q].y);
+            const cx<R> d01 = cmake<R>(r01.x + h01 * g00[q].x + h11 * g01[q].x, r01.y + h01 * g00[q].y + h11 * g01[q].y);
+            const cx<R> d11 = cmake<R>(r11.x + h01 * g10[q].x + h11 * g11[q].x, r11.y + h01 * g10[q].y + h11 * g11[q].y);
+            err2 = fmax(err2, fmax(fmax(d00.x * d00.x + d00.y * d00.y, d01.x * d01.x + d01.y * d01.y),
+                                   fmax(d10.x * d10.x + d10.y * d10.y, d11.x * d11.x + d11.y * d11.y)));
             c00 = fmax(c00, g00[q].x * g00[q].x + g00[q].y * g00[q].y);
             c10 = fmax(c10, g10[q].x * g10[q].x + g10[q].y * g10[q].y);
             c01m = fmax(c01m, g01[q].x * g01[q].x + g01[q].y * g01[q].y);
             c11m = fmax(c11m, g11[q].x * g11[q].x + g11[q].y * g11[q].y);
-            g00[q] = n00; g01[q] = n01; g10[q] = n10; g11[q] = n11;
+            g00[q] = cadd(g00[q], d00); g01[q] = cadd(g01[q], d01);
+            g10[q] = cadd(g10[q], d10); g11[q] = cadd(g11[q], d11);
         }
     }
     stat[0] = err2; stat[1] = rest2; stat[2] = c00; stat[3] = c10; stat[4] = c01m; stat[5] = c11m;
@@ -291,16 +301,15 @@ struct PlusWindowDefect {
     float* lag0;
     __device__ __forceinline__ cx<float> operator()(int bb, int k, cx<float> z) const {
         if (k == 0) {
-            const float h = 0.5f * inv_n;
             if (bb == 0) {
                 lag0[0] = z.x * inv_n;
                 lag0[2] = z.y * inv_n;
-                return cmake<float>(z.x * h, z.y * h);
+                return cmake<float>(z.x * 0.5f, z.y * 0.5f);
             }
             lag0[1] = z.x * inv_n;
-            return cmake<float>(z.x * h, 0.f);
+            return cmake<float>(z.x * 0.5f, 0.f);
         }
-        return cmake<float>(z.x * inv_n, z.y * inv_n);
+        return z;
     }
 };
 
@@ -341,28 +350,30 @@ __device__ __forceinline__ void herm_iteration_defect(const GACC gacc,
                                                       cx<float>* ZB, const ScFftPlan& plan, const cx<float>* tw, int N,
                                                       int fnn, float* lag0, double (&stat)[6],
                                                       const typename FFT::TwRegs* twr = nullptr) {
-    const double dr0 = (double)r0, dr1 = (double)r1;
-    const double k00 = dr0 * dr0, k11 = dr1 * dr1, k01 = dr0 * dr1;
+    const double dr0 = (double)r0, dr1 = (double)r1;  // powers of two: G' = D G is exact
 #pragma unroll
     for (int q = 0; q < FPT; ++q) {
         const int f = threadIdx.x + q * kThreads;
         if (f < fnn) {
             cd G00, G01, G10, G11;
             gacc.load(q, f, G00, G01, G10, G11);
-            // residual R = S - G G^H in fp64, scaled: R' = D R D
+            // scaled factor G' = D G (exact) and the scaled residual R' = S' - G' G'^H in fp64 (s00, s11, s01 hold
+            // S' = D S D, scaled in place by the caller)
+            G00.x *= dr0; G00.y *= dr0; G01.x *= dr0; G01.y *= dr0;
+            G10.x *= dr1; G10.y *= dr1; G11.x *= dr1; G11.y *= dr1;
             const double n00 = G00.x * G00.x + G00.y * G00.y + G01.x * G01.x + G01.y * G01.y;
             const double n11 = G10.x * G10.x + G10.y * G10.y + G11.x * G11.x + G11.y * G11.y;
             const double n01x = G00.x * G10.x + G00.y * G10.y + G01.x * G11.x + G01.y * G11.y;
             const double n01y = G00.y * G10.x - G00.x * G10.y + G01.y * G11.x - G01.x * G11.y;
-            const float a = (float)(((double)s00[q] - n00) * k00), d = (float)(((double)s11[q] - n11) * k11);
-            const cx<float> c = cmake<float>((float)(((double)s01[q].x - n01x) * k01), (float)(((double)s01[q].y - n01y) * k01));
-            // scaled factor G' = D G and its inverse in fp32
-            const cx<float> f00 = cmake<float>((float)(G00.x * dr0), (float)(G00.y * dr0));
-            const cx<float> f01 = cmake<float>((float)(G01.x * dr0), (float)(G01.y * dr0));
-            const cx<float> f10 = cmake<float>((float)(G10.x * dr1), (float)(G10.y * dr1));
-            const cx<float> f11 = cmake<float>((float)(G11.x * dr1), (float)(G11.y * dr1));
+            const float a = (float)((double)s00[q] - n00), d = (float)((double)s11[q] - n11);
+            const cx<float> c = cmake<float>((float)((double)s01[q].x - n01x), (float)((double)s01[q].y - n01y));
+            // its fp32 image and inverse
+            const cx<float> f00 = cmake<float>((float)G00.x, (float)G00.y);
+            const cx<float> f01 = cmake<float>((float)G01.x, (float)G01.y);
+            const cx<float> f10 = cmake<float>((float)G10.x, (float)G10.y);
+            const cx<float> f11 = cmake<float>((float)G11.x, (float)G11.y);
             const cx<float> det = csub(cmul(f00, f11), cmul(f01, f10));
-            const float dn = 1.0f / (det.x * det.x + det.y * det.y);
+            const float dn = RealOps<float>::rcp(det.x * det.x + det.y * det.y);
             const cx<float> idet = cmake<float>(det.x * dn, -det.y * dn);
             const cx<float> u0 = cmul(f11, idet), u1 = cmul(f01, idet);   // row 0 of G'^-1 = (u0, -u1)
             const cx<float> v0 = cmul(f10, idet), v1 = cmul(f00, idet);   // row 1 of G'^-1 = (-v0, v1)
@@ -413,6 +424,7 @@ __device__ __forceinline__ void herm_iteration_defect(const GACC gacc,
     float err_r0 = 0.f, err_r1 = 0.f, rest_r0 = 0.f, rest_r1 = 0.f, c00 = 0.f, c10 = 0.f, c01m = 0.f, c11m = 0.f;
     const float h00 = 0.5f * lag0[0], h01 = 0.5f * lag0[1], h11 = 0.5f * lag0[2];  // P0 - I
     const double i0 = 1.0 / dr0, i1 = 1.0 / dr1;
+    const float hn = 0.5f / (float)N;  // the transforms come back scaled by N (see PlusWindowDefect)
 #pragma unroll
     for (int q = 0; q < FPT; ++q) {
         const int f = threadIdx.x + q * kThreads;
@@ -420,10 +432,10 @@ __device__ __forceinline__ void herm_iteration_defect(const GACC gacc,
             const int fm = f == 0 ? 0 : N - f;
             const cx<float> a1 = Q[f], m1 = Q[fm], a2 = Q[N + f], m2 = Q[N + fm];
             // [E]+ : Y1 = P00 + i P11, Y2 = P01 + i P10 (spectra of real sequences)
-            const cx<float> p00 = cmake<float>(0.5f * (a1.x + m1.x), 0.5f * (a1.y - m1.y));
-            const cx<float> p11 = cmake<float>(0.5f * (a1.y + m1.y), 0.5f * (m1.x - a1.x));
-            const cx<float> p01 = cmake<float>(0.5f * (a2.x + m2.x), 0.5f * (a2.y - m2.y));
-            const cx<float> p10 = cmake<float>(0.5f * (a2.y + m2.y), 0.5f * (m2.x - a2.x));
+            const cx<float> p00 = cmake<float>(hn * (a1.x + m1.x), hn * (a1.y - m1.y));
+            const cx<float> p11 = cmake<float>(hn * (a1.y + m1.y), hn * (m1.x - a1.x));
+            const cx<float> p01 = cmake<float>(hn * (a2.x + m2.x), hn * (a2.y - m2.y));
+            const cx<float> p10 = cmake<float>(hn * (a2.y + m2.y), hn * (m2.x - a2.x));
             cd G00, G01, G10, G11;
             gacc.load(q, f, G00, G01, G10, G11);
             const cx<float> f00 = cmake<float>((float)(G00.x * dr0), (float)(G00.y * dr0));
@@ -596,8 +608,17 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
             bool converged = false;
             int it0 = 0;
             // row scales D = diag(a00, a11)^-1/2 of the fp32 arithmetic (fp32 phase and defect iterations)
-            const float r0 = (float)(1.0 / sqrt(a00)), r1 = (float)(1.0 / sqrt(a11));
+            // POWERS OF TWO (so that S' and G' = D G are exact): r = 2^-floor(e/2) for a = m 2^e, m in [0.5, 1)
+            int e0, e1;
+            frexp(a00, &e0);
+            frexp(a11, &e1);
+            const float r0 = ldexpf(1.f, max(-60, min(60, -(e0 >> 1)))), r1 = ldexpf(1.f, max(-60, min(60, -(e1 >> 1))));
             if (MIXED || (p.tw32 && p.mixed)) {
+                // S' = D S D in place (exact); the next problem's prefetch overwrites the registers anyway
+#pragma unroll
+                for (int q = 0; q < FPT; ++q) {
+                    s00[q] *= r0 * r0; s11[q] *= r1 * r1; s01[q].x *= r0 * r1; s01[q].y *= r0 * r1;
+                }
                 // ---- fp32 phase: the same iteration on the row-scaled problem S' = D S D, G' = D G with
                 // D = diag(a00, a11)^-1/2 (the iteration is equivariant under a left diagonal scaling, so
                 // this only keeps every intermediate O(1) in single precision).  It stops as soon as the
@@ -612,7 +633,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
                 const int cap = p.max_iter < kMaxF32Iters ? p.max_iter : kMaxF32Iters;
                 for (; it0 < cap; ++it0) {
                     float stf[6];
-                    herm_iteration<float, FPT, FFT, kRT>(f00, f01, f10, f11, s00, s11, s01, r0 * r0, r1 * r1, r0 * r1, ZAf,
+                    herm_iteration<float, FPT, FFT, kRT>(f00, f01, f10, f11, s00, s11, s01, 1.f, 1.f, 1.f, ZAf,
                                                          ZBf, p.plan, twsf, N, fnn, lag0f_sh, stf, &twr);
                     // update minus its constant-matrix (tail) part; the barrier inside also fences the buffers
                     const float errf = sqrtf(block_max_nonneg(stf[1], redf, phase_f));
@@ -621,7 +642,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
                         break;
                     }
                 }
-                const double u0 = sqrt(a00), u1 = sqrt(a11);
+                const double u0 = 1.0 / (double)r0, u1 = 1.0 / (double)r1;
 #pragma unroll
                 for (int q = 0; q < FPT; ++q) {
                     const int f = threadIdx.x + q * kThreads;
