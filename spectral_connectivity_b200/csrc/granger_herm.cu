@@ -484,8 +484,17 @@ __device__ __forceinline__ void herm_iteration_defect(const GACC gacc,
 // MIXED = the launcher knows the call is in mixed-precision mode: like LEAN only the fp32 ping-pong buffers and tables
 // are allocated (40 KB instead of 88 KB at nfft = 1000) and the plain fp64 iteration is compiled out, but the fp64
 // factor of the defect iterations stays in registers.
-template <int FPT, typename FFT, bool LEAN, bool MIXED = false>
+//
+// GROUPED (all pairs, S % 4 == 0, MIXED): a CTA works through GROUPS (window b, row i, four columns j0..j0+3 with
+// j0 % 4 == 0, members j > i) instead of single pairs.  The strided gathers of a problem -- 501 bins x 5 values, every
+// one in a different matrix, i.e. one 32-byte sector per 4 or 8 useful bytes, with a measured L1 hit rate of 2 % --
+// are replaced by ONE staging pass per group: per bin the 32-byte sector S[i][j0..j0+3] (two 16-byte loads), the
+// 16-byte power[j0..j0+3], the members' S[j][j] and S[i][i], power[i]: 9 loads instead of 20 and 8 sectors instead of
+// 20 per bin and group.  Every thread stages exactly the bins it later consumes, so no barrier is needed.  The
+// row outputs out[i][j0..j0+3] are collected in shared memory and written as one 16-byte store per bin.
+template <int FPT, typename FFT, bool LEAN, bool MIXED = false, bool GROUPED = false>
 __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(const W2Params p) {
+    static_assert(!GROUPED || (MIXED && !LEAN), "the grouped problem order exists for the mixed-precision kernel only");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[6 * kWarps];
     __shared__ double tail_sh[3];
@@ -515,6 +524,13 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
     cd* G64 = reinterpret_cast<cd*>(
         smem_raw + ((((size_t)4 * N + (kRT ? 0 : FFT::tw_entries(N))) * sizeof(cx<float>) + 15) & ~(size_t)15));
     const GSmem gsm = {G64, gstride};
+    // GROUPED: staging area behind the fp32 buffers and tables (G64 is not used by this variant)
+    float4* stS = reinterpret_cast<float4*>(G64);   // [fnn][2]  S[i][j0..j0+3] (4 complex)
+    float4* stPj = stS + 2 * (size_t)fnn;           // [fnn]     power[j0..j0+3]
+    float4* stDj = stPj + fnn;                      // [fnn]     Re S[j][j], j = j0..j0+3
+    float4* stOut = stDj + fnn;                     // [fnn]     out[i][j0..j0+3]
+    float* stPi = reinterpret_cast<float*>(stOut + fnn);  // [fnn] power[i]
+    float* stDi = stPi + fnn;                       // [fnn]     Re S[i][i]
     typename FFT::TwRegs twr;
     if constexpr (kRT) FFT::load_regs(twr, p.tw32);
     else if (p.tw32) FFT::template fill<float>(twsf, p.tw32, N);
@@ -563,12 +579,99 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
     auto next_prob = [&](long long pr) {
         return ((pr + 1) % kGroup != 0) ? pr + 1 : (pr / kGroup + gridDim.x) * kGroup;
     };
-    if (first < nprob) {
-        pair_of(first, b, pk, pi, pj);
-        load_s(b, pi, pj);
+    // ---- GROUPED problem order: groups (b, i, jb) with jb = j0 / 4 in [(i + 1) / 4, S / 4) ----
+    const int S4 = (int)(p.S / 4);
+    // groups of the rows before row i: sum_{r < i} (S4 - (r + 1) / 4) = i S4 - (2 q (q - 1) + q (r + 1)), i = 4 q + r
+    auto groups_before = [&](int i) -> long long {
+        const long long q4 = i >> 2, r4 = i & 3;
+        return (long long)i * S4 - (2 * q4 * (q4 - 1) + q4 * (r4 + 1));
+    };
+    const long long groups_per_window = GROUPED ? groups_before((int)p.S - 1) : 0;
+    const long long ngroups = groups_per_window * p.B;
+    int j0 = 0, jlo = 0;
+    auto begin_group = [&](long long g) {
+        b = g / groups_per_window;
+        const long long gw = g - b * groups_per_window;
+        int lo = 0, hi = (int)p.S - 2;          // largest row i with groups_before(i) <= gw
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (groups_before(mid) <= gw) lo = mid;
+            else hi = mid - 1;
+        }
+        pi = lo;
+        j0 = 4 * ((pi + 1) / 4 + (int)(gw - groups_before(pi)));
+        jlo = j0 > pi ? j0 : pi + 1;
+        // stage: every thread loads the bins it consumes itself (no barrier)
+#pragma unroll
+        for (int q = 0; q < FPT; ++q) {
+            const int f = threadIdx.x + q * kThreads;
+            if (f < fnn) {
+                const float2* m = reinterpret_cast<const float2*>(p.csm) + ((size_t)b * p.F + f) * p.S * p.S;
+                const float4* row = reinterpret_cast<const float4*>(m + (size_t)pi * p.S + j0);
+                stS[2 * f] = __ldg(row);
+                stS[2 * f + 1] = __ldg(row + 1);
+                const float* pw = p.power + ((size_t)b * p.F + f) * p.S;
+                stPj[f] = __ldg(reinterpret_cast<const float4*>(pw + j0));
+                stPi[f] = __ldg(pw + pi);
+                stDi[f] = __ldg(&m[(size_t)pi * p.S + pi]).x;
+                float4 dj = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (jlo <= j0) dj.x = __ldg(&m[(size_t)j0 * p.S + j0]).x;
+                if (jlo <= j0 + 1) dj.y = __ldg(&m[(size_t)(j0 + 1) * p.S + j0 + 1]).x;
+                if (jlo <= j0 + 2) dj.z = __ldg(&m[(size_t)(j0 + 2) * p.S + j0 + 2]).x;
+                dj.w = __ldg(&m[(size_t)(j0 + 3) * p.S + j0 + 3]).x;
+                stDj[f] = dj;
+            }
+        }
+    };
+    // write the collected row outputs out[i][jlo..j0+3] of the finished group
+    auto flush_group = [&]() {
+        float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+        for (int q = 0; q < FPT; ++q) {
+            const int f = threadIdx.x + q * kThreads;
+            if (f < fnn) {
+                float* dst = out + (((size_t)b * fnn + f) * p.S + pi) * p.S + j0;
+                const float4 v = stOut[f];
+                if (jlo == j0) {
+                    *reinterpret_cast<float4*>(dst) = v;
+                } else {
+                    if (jlo <= j0 + 1) dst[1] = v.y;
+                    if (jlo <= j0 + 2) dst[2] = v.z;
+                    dst[3] = v.w;
+                }
+            }
+        }
+    };
+    long long grp = blockIdx.x, prob = first;
+    bool have;
+    if constexpr (GROUPED) {
+        have = grp < ngroups;
+        if (have) {
+            begin_group(grp);
+            pj = jlo;
+        }
+    } else {
+        have = first < nprob;
+        if (have) {
+            pair_of(first, b, pk, pi, pj);
+            load_s(b, pi, pj);
+        }
     }
-    for (long long prob = first; prob < nprob; prob = next_prob(prob), b = nb_, pk = npk, pi = npi, pj = npj) {
-        if (!FFT::kPrefetch && prob != first) {
+    while (have) {
+        if constexpr (GROUPED) {
+            pk = (long long)pi * (2 * p.S - pi - 1) / 2 + (pj - pi - 1);  // index of (i, j) in combinations(range(S), 2)
+            const int c = pj - j0;
+#pragma unroll
+            for (int q = 0; q < FPT; ++q) {
+                const int f = threadIdx.x + q * kThreads;
+                s00[q] = 0.f; s11[q] = 0.f; s01[q] = make_float2(0.f, 0.f);
+                if (f < fnn) {
+                    s00[q] = stDi[f];
+                    s11[q] = reinterpret_cast<const float*>(stDj + f)[c];
+                    s01[q] = reinterpret_cast<const float2*>(stS + 2 * f)[c];
+                }
+            }
+        } else if (!FFT::kPrefetch && prob != first) {
             pair_of(prob, b, pk, pi, pj);
             load_s(b, pi, pj);
         }
@@ -744,7 +847,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
         // the spectrum registers are free now: fetch the next problem's S under the epilogue
         const int cpi = pi, cpj = pj;
         const long long cb = b;
-        if (FFT::kPrefetch && next_prob(prob) < nprob) {
+        if (!GROUPED && FFT::kPrefetch && next_prob(prob) < nprob) {
             pair_of(next_prob(prob), nb_, npk, npi, npj);
             load_s(nb_, npi, npj);
         }
@@ -752,11 +855,11 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
         if (flag & SC_FLAG_NOT_SPD) {
             for (int f = threadIdx.x; f < fnn; f += kThreads) {
                 float* m = out + ((size_t)cb * fnn + f) * p.S * p.S;
-                m[(size_t)cpi * p.S + cpj] = fnan;
+                if constexpr (GROUPED) reinterpret_cast<float*>(stOut + f)[cpj - j0] = fnan;
+                else m[(size_t)cpi * p.S + cpj] = fnan;
                 m[(size_t)cpj * p.S + cpi] = fnan;
             }
-            continue;
-        }
+        } else {
         // ---- Granger epilogue (connectivity.py:1705-1709, 1739-1748, 1847-1848, 1773-1779) ----
         float pw_i[FPT], pw_j[FPT];
         double h[4] = {0.0, 0.0, 0.0, 0.0};
@@ -765,8 +868,13 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
             const int f = threadIdx.x + q * kThreads;
             pw_i[q] = 0.f; pw_j[q] = 0.f;
             if (f < fnn) {
-                pw_i[q] = __ldg(&p.power[((size_t)cb * p.F + f) * p.S + cpi]);
-                pw_j[q] = __ldg(&p.power[((size_t)cb * p.F + f) * p.S + cpj]);
+                if constexpr (GROUPED) {
+                    pw_i[q] = stPi[f];
+                    pw_j[q] = reinterpret_cast<const float*>(stPj + f)[cpj - j0];
+                } else {
+                    pw_i[q] = __ldg(&p.power[((size_t)cb * p.F + f) * p.S + cpi]);
+                    pw_j[q] = __ldg(&p.power[((size_t)cb * p.F + f) * p.S + cpj]);
+                }
                 const double w = (f == 0 || 2 * f == N) ? 1.0 : 2.0;
                 cd A, B, C, D;
                 gload(q, f, A, B, C, D);
@@ -793,9 +901,27 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
                 const float gc01 = log_ratio((double)pw_i[q], r01 * (t01.x * t01.x + t01.y * t01.y));
                 const float gc10 = log_ratio((double)pw_j[q], r10 * (t10.x * t10.x + t10.y * t10.y));
                 float* m = out + ((size_t)cb * fnn + f) * p.S * p.S;
-                m[(size_t)cpi * p.S + cpj] = gc01;
+                if constexpr (GROUPED) reinterpret_cast<float*>(stOut + f)[cpj - j0] = gc01;
+                else m[(size_t)cpi * p.S + cpj] = gc01;
                 m[(size_t)cpj * p.S + cpi] = gc10;
             }
+        }
+        }  // !NOT_SPD
+        // ---- next problem ----
+        if constexpr (GROUPED) {
+            if (++pj > j0 + 3) {
+                flush_group();
+                grp += gridDim.x;
+                have = grp < ngroups;
+                if (have) {
+                    begin_group(grp);
+                    pj = jlo;
+                }
+            }
+        } else {
+            prob = next_prob(prob);
+            b = nb_; pk = npk; pi = npi; pj = npj;
+            have = prob < nprob;
         }
     }
     if (p.exec_counters && threadIdx.x == 0) {
@@ -808,27 +934,28 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
 
 size_t herm_smem(int nfft) { return (size_t)5 * nfft * sizeof(cd) + (size_t)nfft * 8; }  // ZA, ZB, twiddles (f64 + f32)
 
-template <int FPT, typename FFT, bool LEAN, bool MIXED = false>
+template <int FPT, typename FFT, bool LEAN, bool MIXED = false, bool GROUPED = false>
 int herm_launch_as(W2Params& p, cudaStream_t st) {
     const int fnn = p.nfft / 2 + 1;
     const size_t f32 = (((size_t)4 * p.nfft + (LEAN && FFT::kRegTw ? 0 : FFT::tw_entries(p.nfft))) * sizeof(cx<float>) + 15) & ~(size_t)15;
-    const size_t smem = MIXED ? f32 : LEAN ? f32 + (size_t)4 * fnn * sizeof(cd)
+    const size_t smem = GROUPED ? f32 + (size_t)fnn * 88  // staging: 5 float4 + 2 float per bin
+                        : MIXED ? f32 : LEAN ? f32 + (size_t)4 * fnn * sizeof(cd)
                              : (size_t)(4 * p.nfft + FFT::tw_entries(p.nfft)) * sizeof(cd) +
                                    (size_t)FFT::tw_entries(p.nfft) * sizeof(cx<float>);
     if (smem > 48 * 1024)
-        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT, LEAN, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT, LEAN, MIXED, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem));
     if (const char* e = getenv("SC_GRANGER_CARVEOUT"))  // experiment hook: shared-memory carveout in percent
-        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT, LEAN, MIXED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        SC_CUDA_OK(cudaFuncSetAttribute(granger_herm_kernel<FPT, FFT, LEAN, MIXED, GROUPED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                         atoi(e)));
     int per_sm = 1;
-    SC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, granger_herm_kernel<FPT, FFT, LEAN, MIXED>, kThreads, smem));
+    SC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, granger_herm_kernel<FPT, FFT, LEAN, MIXED, GROUPED>, kThreads, smem));
     if (per_sm < 1) per_sm = 1;
     const long long nprob = p.B * p.n_pairs;
     long long grid = (long long)sc_num_sms() * per_sm;
-    const long long ngroups = (nprob + kGroup - 1) / kGroup;
+    const long long ngroups = GROUPED ? nprob / 4 + 1 : (nprob + kGroup - 1) / kGroup;
     if (grid > ngroups) grid = ngroups;
-    granger_herm_kernel<FPT, FFT, LEAN, MIXED><<<(unsigned)grid, kThreads, smem, st>>>(p);
+    granger_herm_kernel<FPT, FFT, LEAN, MIXED, GROUPED><<<(unsigned)grid, kThreads, smem, st>>>(p);
     SC_LAUNCH_OK();
     return SC_OK;
 }
@@ -843,7 +970,13 @@ int herm_launch(W2Params& p, cudaStream_t st) {
     // the default and the lean one is kept behind SC_GRANGER_LEAN=1 for the record.
     const char* lean = getenv("SC_GRANGER_LEAN");
     if (FFT::kRegTw && p.tw32 && p.mixed && lean && lean[0] == '1') return herm_launch_as<FPT, FFT, true>(p, st);
-    if (p.tw32 && p.mixed) return herm_launch_as<FPT, FFT, false, true>(p, st);
+    if (p.tw32 && p.mixed) {
+        // all pairs of a signal count that keeps the 16-byte row segments aligned -> grouped problem order
+        const char* ng = getenv("SC_GRANGER_NO_GROUPS");
+        if (!p.pairs && p.S % 4 == 0 && p.S >= 8 && p.n_pairs == p.S * (p.S - 1) / 2 && !(ng && ng[0] == '1'))
+            return herm_launch_as<FPT, FFT, false, true, true>(p, st);
+        return herm_launch_as<FPT, FFT, false, true>(p, st);
+    }
     return herm_launch_as<FPT, FFT, false>(p, st);
 }
 

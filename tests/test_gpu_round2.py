@@ -223,3 +223,22 @@ def test_delay_and_group_delay_vs_live_reference(sc):
         ref = g[key]
         assert got.shape == ref.shape and np.array_equal(np.isnan(got), np.isnan(ref)), key
         assert_parity(np.nan_to_num(got), np.nan_to_num(ref), TOL, key)
+
+
+@pytest.mark.parametrize("n_sig,n,fs", [(8, 1000, 1000.0), (12, 1000, 1000.0), (20, 120, 2000.0), (16, 64, 500.0)])
+def test_granger_grouped_problem_order_is_bit_identical(sc, n_sig, n, fs, monkeypatch):
+    """The grouped problem order of the pairwise Granger kernel (one staging pass per (window, row, 4 columns), row
+    outputs written as 16-byte stores) only changes how the spectra reach the registers: results, iteration counts and
+    flags must equal the pair-by-pair order bit for bit -- including rows whose first group straddles the diagonal."""
+    x = O.synthetic_series(3 * n, 6, n_sig, fs, seed=n_sig)
+    kw = dict(sampling_frequency=fs, time_halfbandwidth_product=3, time_window_duration=n / fs)
+    c = sc.Connectivity.from_multitaper(sc.Multitaper(x, **kw), output="torch")
+    monkeypatch.setenv("SC_GRANGER_NO_GROUPS", "1")
+    ref = c.pairwise_spectral_granger_prediction().cpu().numpy()
+    it_ref, ex_ref = c.last_granger_iterations.cpu().numpy().copy(), c.last_granger_executed.tolist()
+    monkeypatch.delenv("SC_GRANGER_NO_GROUPS")
+    got = c.pairwise_spectral_granger_prediction().cpu().numpy()
+    assert np.array_equal(got, ref, equal_nan=True)
+    assert np.array_equal(c.last_granger_iterations.cpu().numpy(), it_ref)
+    assert c.last_granger_executed.tolist() == ex_ref
+    assert np.isfinite(got[..., 0, 1]).all() and np.isnan(got[..., 0, 0]).all()
