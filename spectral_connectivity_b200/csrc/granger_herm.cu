@@ -496,7 +496,8 @@ template <int FPT, typename FFT, bool LEAN, bool MIXED = false, bool GROUPED = f
 __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(const W2Params p) {
     static_assert(!GROUPED || (MIXED && !LEAN), "the grouped problem order exists for the mixed-precision kernel only");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[6 * kWarps];
+    __shared__ double red4[2 * 4 * kWarps];
+    int phase_s = 0;
     __shared__ double tail_sh[3];
     __shared__ int tail_it[2];
     __shared__ unsigned redf[2 * kWarps];
@@ -675,7 +676,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
             pair_of(prob, b, pk, pi, pj);
             load_s(b, pi, pj);
         }
-        double a[3] = {0.0, 0.0, 0.0};
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int q = 0; q < FPT; ++q) {
             const int f = threadIdx.x + q * kThreads;
@@ -684,9 +685,10 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
                 a[0] += w * s00[q]; a[1] += w * s01[q].x; a[2] += w * s11[q];
             }
         }
-        block_sum<3>(a, red);
+        block_sum4(a, red4, phase_s);
         // ---- Cholesky of the real lag-0 covariance, G0 = L^T (mpd.py:75-77) ----
-        const double a00 = a[0] / N, a10 = a[1] / N, a11 = a[2] / N;
+        const double inv_nd = 1.0 / (double)N;
+        const double a00 = a[0] * inv_nd, a10 = a[1] * inv_nd, a11 = a[2] * inv_nd;
         const double l00 = sqrt(a00), l10 = a10 / l00, d11 = a11 - l10 * l10, l11 = sqrt(d11);
         int flag = 0, it_done = 0;
         if (!(a00 > 0.0) || !(d11 > 0.0) || !isfinite(l00) || !isfinite(l11)) flag = SC_FLAG_NOT_SPD;
@@ -745,7 +747,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
                         break;
                     }
                 }
-                const double u0 = 1.0 / (double)r0, u1 = 1.0 / (double)r1;
+                const double u0 = (double)(1.f / r0), u1 = (double)(1.f / r1);  // powers of two: exact
 #pragma unroll
                 for (int q = 0; q < FPT; ++q) {
                     const int f = threadIdx.x + q * kThreads;
@@ -881,12 +883,13 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
                 h[0] += w * A.x; h[1] += w * B.x; h[2] += w * C.x; h[3] += w * D.x;
             }
         }
-        block_sum<4>(h, red);
-        const double h00 = h[0] / N, h01 = h[1] / N, h10 = h[2] / N, h11 = h[3] / N;
+        block_sum4(h, red4, phase_s);
+        const double h00 = h[0] * inv_nd, h01 = h[1] * inv_nd, h10 = h[2] * inv_nd, h11 = h[3] * inv_nd;
         const double lam = kTikhonov * (h00 * h00 + h01 * h01 + h10 * h10 + h11 * h11) * 0.25;
         const double m00 = h00 + lam, m11 = h11 + lam;
         const double mdet = m00 * m11 - h01 * h10;
-        const double v00 = m11 / mdet, v01 = -h01 / mdet, v10 = -h10 / mdet, v11 = m00 / mdet;
+        const double imdet = 1.0 / mdet;
+        const double v00 = m11 * imdet, v01 = -h01 * imdet, v10 = -h10 * imdet, v11 = m00 * imdet;
         const double c00 = h00 * h00 + h01 * h01, c01 = h00 * h10 + h01 * h11, c11 = h10 * h10 + h11 * h11;
         const double r01 = c11 - c01 * c01 / c00;
         const double r10 = c00 - c01 * c01 / c11;

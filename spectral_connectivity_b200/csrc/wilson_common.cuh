@@ -67,6 +67,38 @@ __device__ __forceinline__ void block_sum(double* v, double* red) {
     }
 }
 
+// Block sums of up to FOUR doubles per thread with a transposing butterfly: the first two exchange rounds halve the
+// number of values a lane carries (lane l ends up owning value 2 (l & 1) + ((l >> 1) & 1)), three more rounds finish
+// the warp, four lanes per warp publish, ONE barrier (double-buffered like block_max_nonneg), and the cross-warp
+// stage is again a butterfly over the lane bits that index the warp.  26 shuffles + 9 additions per thread instead of
+// 40 shuffles, 32 shared loads and 52 additions (block_sum<4>): the Granger kernel's fixed part spent 30 % of its
+// instructions there (profiles/r02_ncu_granger_fixed_part.txt).  Every thread returns all four totals.
+__device__ __forceinline__ double shfl_xor_f64(double x, int m) { return __shfl_xor_sync(0xffffffffu, x, m); }
+__device__ __forceinline__ void block_sum4(double (&v)[4], double* red /* [2 * 4 * kWarps] */, int& phase) {
+    static_assert(kWarps <= 8 && (kWarps & (kWarps - 1)) == 0, "the cross-warp butterfly indexes warps by lane bits 2..4");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool b0 = lane & 1, b1 = lane & 2;
+    double k0 = b0 ? v[2] : v[0], k1 = b0 ? v[3] : v[1];
+    k0 += shfl_xor_f64(b0 ? v[0] : v[2], 1);
+    k1 += shfl_xor_f64(b0 ? v[1] : v[3], 1);
+    double k = (b1 ? k1 : k0) + shfl_xor_f64(b1 ? k0 : k1, 2);
+    k += shfl_xor_f64(k, 4);
+    k += shfl_xor_f64(k, 8);
+    k += shfl_xor_f64(k, 16);
+    const int q = 2 * (lane & 1) + ((lane >> 1) & 1);
+    double* r = red + phase * 4 * kWarps;
+    phase ^= 1;
+    if (lane < 4) r[q * kWarps + warp] = k;
+    __syncthreads();
+    k = r[q * kWarps + ((lane >> 2) & (kWarps - 1))];
+#pragma unroll
+    for (int m = 4; m < 4 * kWarps; m <<= 1) k += shfl_xor_f64(k, m);
+    v[0] = __shfl_sync(0xffffffffu, k, 0);
+    v[1] = __shfl_sync(0xffffffffu, k, 2);
+    v[2] = __shfl_sync(0xffffffffu, k, 1);
+    v[3] = __shfl_sync(0xffffffffu, k, 3);
+}
+
 template <int NV>
 __device__ __forceinline__ void block_maxn(double (&v)[NV], double* red) {
 #pragma unroll
