@@ -25,6 +25,8 @@
 // Pipelines: smem ring (full_raw -> full_cvt -> empty) and TMEM ring (tmem_full/tmem_empty), all
 // mbarriers.  Every spin is bounded and traps, so a protocol bug cannot hang the device.
 #include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "sc_common.cuh"
 
@@ -34,6 +36,10 @@ constexpr int TM = 128;                      // tile rows (signal i)
 constexpr int TN = 128;                      // tile cols (signal j)
 constexpr int KC = 16;                       // observations per smem stage
 constexpr int STAGES = 3;
+#ifndef SC_CSM_DRAIN
+#define SC_CSM_DRAIN 1
+#endif
+constexpr int DRAIN = SC_CSM_DRAIN;         // smem stages accumulated in TMEM before the epilogue warps drain them
 constexpr int SLAB = 4 * KC * 128;           // [4 groups of 32 signals][KC][128 B] = 8 KB
 constexpr int STAGE_RAW = 4 * SLAB;          // Ar_I, Ai_I, Ar_J, Ai_J
 constexpr int STAGE_BYTES = 2 * STAGE_RAW;   // + the lo mirror
@@ -68,6 +74,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+#ifdef SC_CSM_PROFILE
+#define PWAIT(acc, bar, par) do { const long long t0_ = clock64(); mbar_wait(bar, par); acc += clock64() - t0_; } while (0)
+#else
+#define PWAIT(acc, bar, par) mbar_wait(bar, par)  // acc only exists in profile builds
+#endif
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
     asm volatile(
@@ -94,17 +105,33 @@ __host__ __device__ constexpr uint32_t umma_idesc(bool neg_a) {
            ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// The MMA warp runs its loop with ALL 32 lanes (warp-uniform control flow and operands) and only the instruction itself
+// is predicated on the elected lane: issued from inside `if (lane == 0)` every tcgen05.mma was wrapped by the compiler
+// in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop that moves its operands into uniform registers (~10 instructions and a
+// backward branch per MMA; measured with per-role cycle counters: the issuing thread was busy 2230 cycles per
+// 24-MMA stage against 1536 cycles of tensor-pipe work, and the tensor pipe idled at 49 %).
+__device__ __forceinline__ uint32_t elect_leader() {
+    uint32_t is_leader;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(is_leader));
+    return is_leader;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc,
+                                          uint32_t leader) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "r"(leader)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(leader)
+        : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -213,8 +240,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) csm_tc_kernel(const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp, elected lane issues) =====================
+        {
+            const uint32_t leader = elect_leader();
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -226,7 +254,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) csm_tc_kernel(const __grid_consta
                 decode_tile(t, p.ntile, bf, ti, tj);
                 const bool diag = ti == tj;
                 for (int kc = 0; kc < nk; ++kc) {
-                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    const bool fresh = kc % DRAIN == 0;                       // first stage of an accumulator
+                    const bool last = kc % DRAIN == DRAIN - 1 || kc == nk - 1;  // ... and its last
+                    if (fresh) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                     mbar_wait(&full_cvt[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_re = tmem_base + (uint32_t)acc * 256u;
@@ -245,31 +275,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) csm_tc_kernel(const __grid_consta
                             if (pass == 0) {
                                 const uint64_t arl = umma_desc(lo + ko), ail = umma_desc(lo + SLAB + ko);
                                 const uint64_t brl = umma_desc(lo + boff + ko), bil = umma_desc(lo + boff + SLAB + ko);
-                                const uint32_t first = ks ? 1u : 0u;  // fresh accumulator every stage
-                                umma_tf32(d_re, arh, brl, idesc, first);
-                                umma_tf32(d_re, arl, brh, idesc, 1u);
-                                umma_tf32(d_re, aih, bil, idesc, 1u);
-                                umma_tf32(d_re, ail, bih, idesc, 1u);
-                                umma_tf32(d_im, aih, brl, idesc, first);
-                                umma_tf32(d_im, ail, brh, idesc, 1u);
-                                umma_tf32(d_im, arh, bil, idesc_neg, 1u);
-                                umma_tf32(d_im, arl, bih, idesc_neg, 1u);
+                                const uint32_t first = (ks || !fresh) ? 1u : 0u;  // fresh accumulator every DRAIN stages
+                                umma_tf32(d_re, arh, brl, idesc, first, leader);
+                                umma_tf32(d_re, arl, brh, idesc, 1u, leader);
+                                umma_tf32(d_re, aih, bil, idesc, 1u, leader);
+                                umma_tf32(d_re, ail, bih, idesc, 1u, leader);
+                                umma_tf32(d_im, aih, brl, idesc, first, leader);
+                                umma_tf32(d_im, ail, brh, idesc, 1u, leader);
+                                umma_tf32(d_im, arh, bil, idesc_neg, 1u, leader);
+                                umma_tf32(d_im, arl, bih, idesc_neg, 1u, leader);
                             } else {
                                 // Re += Ar Br^T + Ai Bi^T ;  Im += Ai Br^T - Ar Bi^T
-                                umma_tf32(d_re, arh, brh, idesc, 1u);
-                                umma_tf32(d_re, aih, bih, idesc, 1u);
-                                umma_tf32(d_im, aih, brh, idesc, 1u);
-                                umma_tf32(d_im, arh, bih, idesc_neg, 1u);
+                                umma_tf32(d_re, arh, brh, idesc, 1u, leader);
+                                umma_tf32(d_re, aih, bih, idesc, 1u, leader);
+                                umma_tf32(d_im, aih, brh, idesc, 1u, leader);
+                                umma_tf32(d_im, arh, bih, idesc_neg, 1u, leader);
                             }
                         }
                     }
-                    umma_commit(&empty_bar[stage]);  // smem stage reusable once these MMAs retire
-                    umma_commit(&tmem_full[acc]);    // and this stage's partial tile can be drained
+                    umma_commit(&empty_bar[stage], leader);  // smem stage reusable once these MMAs retire
+                    if (last) umma_commit(&tmem_full[acc], leader);  // and this partial tile can be drained
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
-                    if (++acc == 2) {
+                    if (last && ++acc == 2) {
                         acc = 0;
                         acc_phase ^= 1;
                     }
@@ -300,7 +330,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) csm_tc_kernel(const __grid_consta
                     h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
                     h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
                     l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+#ifndef SC_CSM_KEEP_RAW_HI
                     raw[idx] = h;
+#endif
                     lo[idx] = l;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -329,7 +361,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) csm_tc_kernel(const __grid_consta
                 sre[u] = 0.f;
                 sim[u] = 0.f;
             }
-            for (int kc = 0; kc < nk; ++kc) {
+            for (int kc = 0; kc < nk; kc += DRAIN) {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)half * 64u;
@@ -370,6 +402,351 @@ __global__ void __launch_bounds__(NTHREADS, 1) csm_tc_kernel(const __grid_consta
         }
     }
 
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+
+// =====================================================================================================================
+// Variant with the A operand in TENSOR MEMORY (default; SC_CSM_TA=0 selects the kernel above).
+//
+// A 128x128x8 tf32 MMA with both operands in shared memory reads 4 KB (A) + 4 KB (B) per 64 clocks = 128 B/clk, the whole
+// shared-memory bandwidth of the SM, so the kernel above can never exceed the share of that bandwidth the TMA writes and
+// the converter warps leave it (measured: tensor pipe 49 %; draining the accumulators 4x less often or dropping the
+// hi write-back moved it by 8 % / 2 %).  Here the converter warps write the hi/lo split of the ROW block straight into
+// TMEM (tcgen05.st, lane = signal row, 8 columns per K step and operand) and the MMAs take A from there
+// (tcgen05.mma [d], [a], b-desc): operand reads from shared memory halve (96 KB instead of 192 KB per 16-observation
+// stage), the row block needs no lo mirror in shared memory, and the hi operand of the column block is the RAW fp32
+// slab (kind::tf32 ignores the low 13 mantissa bits -- measured: results identical to an explicit truncation).
+// TMEM: three 128-column accumulators used as a ring of HALF stages (Re, Im, Re, ...) + two 64-column A buffers.
+// Shared memory: 4 stages of {raw I (re, im), raw J (re, im), lo J (re, im)} = 48 KB.
+#ifndef SC_CSM_TA_STAGES
+#define SC_CSM_TA_STAGES 4
+#endif
+constexpr int TA_STAGES = SC_CSM_TA_STAGES;
+constexpr int TA_STAGE_BYTES = 6 * SLAB;
+constexpr uint32_t TA_ACC_SLOTS = 3;
+constexpr uint32_t TA_A_BASE = 384;  // TMEM column of the first A buffer (2 x 64 columns)
+
+#ifdef SC_CSM_FAKE_KMAJOR  // TIMING EXPERIMENT ONLY (wrong results): B declared K-major, 64-byte swizzle
+__host__ __device__ constexpr uint32_t umma_idesc_ta(bool neg_a) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)(TN >> 3) << 17) |
+           ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ uint64_t umma_desc_b(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+#else
+__host__ __device__ constexpr uint32_t umma_idesc_ta(bool neg_a) {  // A from TMEM (K-major), B MN-major
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((neg_a ? 1u : 0u) << 13) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
+           ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ uint64_t umma_desc_b(uint32_t saddr) { return umma_desc(saddr); }
+#endif
+#ifdef SC_CSM_FAKE_KMAJOR
+constexpr uint32_t TA_KSTEP_BYTES = 32u;
+#else
+constexpr uint32_t TA_KSTEP_BYTES = 1024u;  // 8 observations x 128-byte rows
+#endif
+
+__device__ __forceinline__ void umma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc,
+                                             uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc), "r"(leader)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) csm_tc_ta_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_raw[TA_STAGES], full_cvt[TA_STAGES], empty_bar[TA_STAGES], a_empty[2],
+        acc_full[TA_ACC_SLOTS], acc_empty[TA_ACC_SLOTS];
+    __shared__ uint32_t tmem_base_sh;
+
+    unsigned char* stage_base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = (int)((p.R + KC - 1) / KC);
+#ifdef SC_CSM_PROFILE  // per-role mbarrier wait accounting (tools/csm_role_profile.py)
+    long long w0 = 0, w1 = 0, w2 = 0;
+    const long long tstart = clock64();
+#endif
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TA_STAGES; ++s) {
+            mbar_init(&full_raw[s], 1);
+            mbar_init(&full_cvt[s], CVT_THREADS);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) mbar_init(&a_empty[a], 1);
+        for (int a = 0; a < (int)TA_ACC_SLOTS; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], EPI_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    }
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+                long long bf;
+                int ti, tj;
+                decode_tile(t, p.ntile, bf, ti, tj);
+                const bool diag = ti == tj;
+                for (int kc = 0; kc < nk; ++kc) {
+                    PWAIT(w0, &empty_bar[stage], phase ^ 1);
+                    unsigned char* dst = stage_base + (size_t)stage * TA_STAGE_BYTES;
+                    mbar_expect_tx(&full_raw[stage], (diag ? 2 : 4) * SLAB);
+                    const int plane = (int)(bf * 2);
+                    tma_load_4d(dst + 2 * SLAB, &tmap, &full_raw[stage], 0, kc * KC, tj * 4, plane);
+                    tma_load_4d(dst + 3 * SLAB, &tmap, &full_raw[stage], 0, kc * KC, tj * 4, plane + 1);
+                    if (!diag) {
+                        tma_load_4d(dst, &tmap, &full_raw[stage], 0, kc * KC, ti * 4, plane);
+                        tma_load_4d(dst + SLAB, &tmap, &full_raw[stage], 0, kc * KC, ti * 4, plane + 1);
+                    }
+                    if (++stage == TA_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (whole warp, elected lane issues) =====================
+        {
+            const uint32_t leader = elect_leader();
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t slot = 0, slot_phase = 0;   // accumulator ring (half stages)
+            uint32_t ab = 0;                     // A buffer of this stage
+            constexpr uint32_t idesc = umma_idesc_ta(false), idesc_neg = umma_idesc_ta(true);
+            for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+                for (int kc = 0; kc < nk; ++kc) {
+                    PWAIT(w0, &full_cvt[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sb = smem_u32(stage_base + (size_t)stage * TA_STAGE_BYTES);
+                    const uint32_t brh_s = sb + 2u * SLAB, bih_s = sb + 3u * SLAB, brl_s = sb + 4u * SLAB, bil_s = sb + 5u * SLAB;
+                    const uint32_t a0 = tmem_base + TA_A_BASE + ab * 64u;  // [ks][Ar_hi, Ar_lo, Ai_hi, Ai_lo][8 columns]
+                    // ---- Re = Ar Br^T + Ai Bi^T: cross terms first (small), then hi*hi ----
+                    PWAIT(w1, &acc_empty[slot], slot_phase ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    {
+                        const uint32_t d = tmem_base + slot * 128u;
+#pragma unroll
+                        for (int ks = 0; ks < KC / 8; ++ks) {
+                            const uint32_t ko = (uint32_t)ks * TA_KSTEP_BYTES, ak = a0 + (uint32_t)ks * 32u;
+                            umma_tf32_ta(d, ak + 0u, umma_desc_b(brl_s + ko), idesc, ks ? 1u : 0u, leader);
+                            umma_tf32_ta(d, ak + 8u, umma_desc_b(brh_s + ko), idesc, 1u, leader);
+                            umma_tf32_ta(d, ak + 16u, umma_desc_b(bil_s + ko), idesc, 1u, leader);
+                            umma_tf32_ta(d, ak + 24u, umma_desc_b(bih_s + ko), idesc, 1u, leader);
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < KC / 8; ++ks) {
+                            const uint32_t ko = (uint32_t)ks * TA_KSTEP_BYTES, ak = a0 + (uint32_t)ks * 32u;
+                            umma_tf32_ta(d, ak + 0u, umma_desc_b(brh_s + ko), idesc, 1u, leader);
+                            umma_tf32_ta(d, ak + 16u, umma_desc_b(bih_s + ko), idesc, 1u, leader);
+                        }
+                        umma_commit(&acc_full[slot], leader);
+                        if (++slot == TA_ACC_SLOTS) {
+                            slot = 0;
+                            slot_phase ^= 1;
+                        }
+                    }
+                    // ---- Im = Ai Br^T - Ar Bi^T ----
+                    PWAIT(w1, &acc_empty[slot], slot_phase ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    {
+                        const uint32_t d = tmem_base + slot * 128u;
+#pragma unroll
+                        for (int ks = 0; ks < KC / 8; ++ks) {
+                            const uint32_t ko = (uint32_t)ks * TA_KSTEP_BYTES, ak = a0 + (uint32_t)ks * 32u;
+                            umma_tf32_ta(d, ak + 16u, umma_desc_b(brl_s + ko), idesc, ks ? 1u : 0u, leader);
+                            umma_tf32_ta(d, ak + 24u, umma_desc_b(brh_s + ko), idesc, 1u, leader);
+                            umma_tf32_ta(d, ak + 0u, umma_desc_b(bil_s + ko), idesc_neg, 1u, leader);
+                            umma_tf32_ta(d, ak + 8u, umma_desc_b(bih_s + ko), idesc_neg, 1u, leader);
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < KC / 8; ++ks) {
+                            const uint32_t ko = (uint32_t)ks * TA_KSTEP_BYTES, ak = a0 + (uint32_t)ks * 32u;
+                            umma_tf32_ta(d, ak + 16u, umma_desc_b(brh_s + ko), idesc, 1u, leader);
+                            umma_tf32_ta(d, ak + 0u, umma_desc_b(bih_s + ko), idesc_neg, 1u, leader);
+                        }
+                        umma_commit(&acc_full[slot], leader);
+                        if (++slot == TA_ACC_SLOTS) {
+                            slot = 0;
+                            slot_phase ^= 1;
+                        }
+                    }
+                    umma_commit(&empty_bar[stage], leader);  // shared-memory stage and A buffer reusable once these MMAs retire
+                    umma_commit(&a_empty[ab], leader);
+                    ab ^= 1u;
+                    if (++stage == TA_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== converter: row block -> TMEM (hi, lo); column block -> lo mirror =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        const int ct = threadIdx.x - 128;            // signal row of the tile = TMEM lane
+        const int g = ct >> 5, sgn = ct & 31;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        int stage = 0;
+        uint32_t phase = 0, ab = 0, ab_phase = 0;
+        for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+            long long bf;
+            int ti, tj;
+            decode_tile(t, p.ntile, bf, ti, tj);
+            const bool diag = ti == tj;
+            for (int kc = 0; kc < nk; ++kc) {
+                PWAIT(w0, &full_raw[stage], phase);
+                unsigned char* sbase = stage_base + (size_t)stage * TA_STAGE_BYTES;
+                const unsigned char* src = sbase + (diag ? 2 * SLAB : 0);  // raw row block (re, then im)
+                PWAIT(w1, &a_empty[ab], ab_phase ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = tmem_base + lane_base + TA_A_BASE + ab * 64u;
+#pragma unroll
+                for (int ks = 0; ks < KC / 8; ++ks) {
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl) {
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = ks * 8 + i;
+                            // TMA box {32 s, KC r, 4 groups}, swizzle 128B with 32-byte atoms: chunk ^= (r & 3)
+                            const float x = *reinterpret_cast<const float*>(
+                                src + pl * SLAB + g * (KC * 128) + r * 128 + ((((sgn >> 3) ^ (r & 3))) << 5) + (sgn & 7) * 4);
+                            const uint32_t h = __float_as_uint(x) & 0xffffe000u;
+                            hi[i] = h;
+                            lo[i] = __float_as_uint(x - __uint_as_float(h));
+                        }
+                        tmem_st8(a0 + (uint32_t)(ks * 32 + pl * 16), hi);
+                        tmem_st8(a0 + (uint32_t)(ks * 32 + pl * 16 + 8), lo);
+                    }
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                // lo mirror of the column block (its hi operand is the raw slab itself)
+                const float4* raw = reinterpret_cast<const float4*>(sbase + 2 * SLAB);
+                float4* lom = reinterpret_cast<float4*>(sbase + 4 * SLAB);
+#pragma unroll 4
+                for (int idx = ct; idx < 2 * SLAB / 16; idx += CVT_THREADS) {
+                    const float4 v = raw[idx];
+                    float4 l;
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                    lom[idx] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&full_cvt[stage]);
+                ab ^= 1u;
+                if (ab == 0) ab_phase ^= 1;
+                if (++stage == TA_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== epilogue / drain =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int half = (warp - 8) >> 2;  // column half of the tile
+        uint32_t slot = 0, slot_phase = 0;
+        for (long long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+            long long bf;
+            int ti, tj;
+            decode_tile(t, p.ntile, bf, ti, tj);
+            const bool diag = ti == tj;
+            float sre[64], sim[64];
+#pragma unroll
+            for (int u = 0; u < 64; ++u) {
+                sre[u] = 0.f;
+                sim[u] = 0.f;
+            }
+            for (int kc = 0; kc < nk; ++kc) {
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {  // 0: Re half stage, 1: Im half stage
+                    PWAIT(w0, &acc_full[slot], slot_phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 128u + (uint32_t)half * 64u;
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(trow, v0);
+                    tmem_ld32(trow + 32, v1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&acc_empty[slot]);
+                    if (part == 0) {
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) {
+                            sre[u] += __uint_as_float(v0[u]);
+                            sre[32 + u] += __uint_as_float(v1[u]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) {
+                            sim[u] += __uint_as_float(v0[u]);
+                            sim[32 + u] += __uint_as_float(v1[u]);
+                        }
+                    }
+                    if (++slot == TA_ACC_SLOTS) {
+                        slot = 0;
+                        slot_phase ^= 1;
+                    }
+                }
+            }
+            const long long i = (long long)ti * TM + q * 32 + lane;
+            const long long j0 = (long long)tj * TN + half * 64;
+            float2* mat = p.out + bf * p.S * p.S;
+#pragma unroll
+            for (int u = 0; u < 64; ++u) {
+                const long long j = j0 + u;
+                const float2 v = make_float2(sre[u] * p.scale, sim[u] * p.scale);
+                if (j < p.S && i < p.S) {
+                    mat[i * p.S + j] = v;
+                    if (!diag) mat[j * p.S + i] = make_float2(v.x, -v.y);  // coalesced across lanes
+                }
+            }
+        }
+    }
+
+#ifdef SC_CSM_PROFILE
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 8))
+        printf("warp %d total %lld wait0 %lld wait1 %lld wait2 %lld stages %lld\n", warp, clock64() - tstart, w0, w1, w2,
+               (long long)nk * ((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x));
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
@@ -438,11 +815,18 @@ int sc_csm_tc_launch(const float* xp, int64_t B, int64_t F, int64_t R, int64_t S
     p.BF = B * F; p.R = R; p.S = S; p.scale = scale; p.out = reinterpret_cast<float2*>(out);
     p.ntile = (int)((S + TM - 1) / TM);
     p.ntiles = p.BF * (long long)(p.ntile * (p.ntile + 1) / 2);
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-    SC_CUDA_OK(cudaFuncSetAttribute(csm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = sc_num_sms();
     if (grid > p.ntiles) grid = p.ntiles;
-    csm_tc_kernel<<<(unsigned)grid, NTHREADS, smem, st>>>(tmap, p);
+    const char* ta = getenv("SC_CSM_TA");  // "0": both operands from shared memory (the first kernel)
+    if (ta && ta[0] == '0') {
+        const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+        SC_CUDA_OK(cudaFuncSetAttribute(csm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        csm_tc_kernel<<<(unsigned)grid, NTHREADS, smem, st>>>(tmap, p);
+    } else {
+        const size_t smem = (size_t)TA_STAGES * TA_STAGE_BYTES + 1024;
+        SC_CUDA_OK(cudaFuncSetAttribute(csm_tc_ta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        csm_tc_ta_kernel<<<(unsigned)grid, NTHREADS, smem, st>>>(tmap, p);
+    }
     SC_LAUNCH_OK();
     return SC_OK;
 }
