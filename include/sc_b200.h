@@ -128,6 +128,11 @@ int sc_nonfinite_flag(const float* x, int64_t n, int* flag, void* stream);
  * second pass over the coefficients that sc_power needs. */
 int sc_power_from_csm(const void* csm_c64, int64_t BF, int64_t S, float* out, void* stream);
 
+/* Packed upper triangle (diagonal included, row-major: (i, j >= i) -> i S - i (i - 1) / 2 + j - i) of a symmetric real
+ * measure [BF][S][S] -> [BF][S (S + 1) / 2]: an opt-in result format that halves the device -> host bytes of
+ * coherence-type results (no reference counterpart: the reference returns the full symmetric array, connectivity.py:675-702). */
+int sc_pack_upper(const float* in, int64_t BF, int64_t S, float* out, void* stream);
+
 /* coherency / coherence_magnitude / coherence_phase / imaginary_coherence (connectivity.py:632-743),
  * phase_locking_value / pairwise_phase_consistency (:905-931, :1129-1159), phase_lag_index,
  * weighted / debiased variants (:933-1127): element-wise epilogues on [B][F][S][S]. */

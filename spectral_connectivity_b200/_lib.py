@@ -26,6 +26,7 @@ SIGNATURES = {
     "sc_power": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_float, _P, _P]),
     "sc_nonfinite_flag": (c_int, [_P, c_int64, _P, _P]),
     "sc_power_from_csm": (c_int, [_P, c_int64, c_int64, _P, _P]),
+    "sc_pack_upper": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "sc_csm": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_float, c_int, _P, _P]),
     "sc_csm_simt": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_float, c_int, _P, _P]),
     "sc_pairwise_epilogue": (c_int, [c_int, _P, _P, c_int64, c_int64, c_int64, c_double, _P, _P]),

@@ -51,6 +51,9 @@ _PAIRWISE = {
 # the live reference).
 _GRANGER_OK = tuple(EXPECTATION_AXES)
 _SYMM_SLOTS = {}  # (group name, device) -> peer-mapped partial-sum buffers of reduce_impl="p2p"
+# real measures that are symmetric in (i, j): may be returned as packed upper triangles (compute(packed=...))
+SYMMETRIC_MEASURES = ("coherence_magnitude", "phase_locking_value", "pairwise_phase_consistency",
+                      "debiased_squared_phase_lag_index", "debiased_squared_weighted_phase_lag_index")
 MEASURES = ("power", "expectation_cross_spectral_matrix", "_phase_locking_value",
             "pairwise_spectral_granger_prediction") + tuple(_PAIRWISE)
 
@@ -575,7 +578,7 @@ class Connectivity:
         return csm
 
     def compute(self, measures, pairs=None, tolerance=1e-8, max_iterations=60, tail_extrapolation=True,
-                mixed_precision=None, out=None):
+                mixed_precision=None, out=None, packed=()):
         """Compute several measures in ONE streaming pass over window chunks.
 
         ``measures``: iterable of names from ``MEASURES``.  Returns {name: array}.  Per chunk
@@ -593,9 +596,20 @@ class Connectivity:
         ``out`` (output="numpy" only): {name: pinned host array from ``pinned_empty``} to receive results, so that
         a pipeline calling ``compute`` repeatedly does not allocate (and page-lock) gigabytes per call.
 
+        ``packed``: names from ``SYMMETRIC_MEASURES`` to return as packed upper triangles, shape
+        (..., n_frequencies, S (S + 1) / 2) with element (i, j >= i) at ``i S - i (i - 1) / 2 + j - i`` (diagonal
+        included; ``unpack_upper`` restores the full array).  An opt-in format without a reference counterpart: it
+        halves the device -> host bytes of those results, which is what bounds an end-to-end pass once the kernels are
+        faster than the host link.
+
         With ``reduce_mode="reduce_scatter"`` the results hold this rank's windows only (``owned_windows``)."""
         lib = _lib.load()
         measures = list(measures)
+        packed = tuple(packed or ())
+        for name in packed:
+            if name not in SYMMETRIC_MEASURES or name not in measures:
+                raise ValueError(f"packed: '{name}' is not a requested symmetric measure "
+                                 f"(symmetric measures: {', '.join(SYMMETRIC_MEASURES)})")
         if mixed_precision is None:
             mixed_precision = not self._fp64_wilson
         for name in measures:
@@ -637,6 +651,9 @@ class Connectivity:
             else:
                 res[name] = torch.empty((n_batch, n_freq, n_sig, n_sig), dtype=torch.float32, device=dev)
 
+        tri = n_sig * (n_sig + 1) // 2
+        res_packed = {name: torch.empty((n_batch, n_freq, tri), dtype=torch.float32, device=dev) for name in packed}
+
         pair_t = None
         n_pairs = n_sig * (n_sig - 1) // 2
         if want_granger:
@@ -663,7 +680,7 @@ class Connectivity:
         if self._output == "numpy":
             copy_stream = _lib.side_stream(dev, "d2h")
             for name, t in res.items():
-                shp = (t.shape[0], fnn) + tuple(t.shape[2:])
+                shp = (t.shape[0], fnn) + (tuple(t.shape[2:]) if name not in res_packed else (tri,))
                 given = None if out is None else out.get(name)
                 if given is not None:
                     g = given if isinstance(given, torch.Tensor) else torch.from_numpy(given)
@@ -683,7 +700,7 @@ class Connectivity:
             ev.record()
             copy_stream.wait_event(ev)
             with torch.cuda.stream(copy_stream):
-                host[name][b0:b1].copy_(res[name][b0:b1, :fnn], non_blocking=True)
+                host[name][b0:b1].copy_(res_packed.get(name, res[name])[b0:b1, :fnn], non_blocking=True)
 
         st = _lib.stream_ptr()
         # reduce_impl="p2p": the first coherence-family measure is produced by the peer-reduce kernel itself
@@ -714,6 +731,9 @@ class Connectivity:
                     continue
                 src_kind, code, _ = _PAIRWISE[name]
                 if name == fused_name and item.get("fused"):
+                    if name in res_packed:
+                        _lib.check(lib.sc_pack_upper(_lib.ptr(res[name][b0:b1]), nb * n_freq, n_sig,
+                                                     _lib.ptr(res_packed[name][b0:b1]), st), "sc_pack_upper")
                     offload(name, b0, b1)
                     continue
                 src = {"csm": csm, "plv": plv, "pli": pli}[src_kind]
@@ -725,6 +745,9 @@ class Connectivity:
                                                         _lib.ptr(power) if src_kind == "csm" else None, nb, n_freq,
                                                         n_sig, float(self.n_observations), _lib.ptr(dst), st),
                                f"sc_pairwise_epilogue[{name}]")
+                    if name in res_packed:
+                        _lib.check(lib.sc_pack_upper(_lib.ptr(dst), nb * n_freq, n_sig, _lib.ptr(res_packed[name][b0:b1]),
+                                                     st), "sc_pack_upper")
                 offload(name, b0, b1)
             if want_granger:
                 it_c = torch.zeros((n_pairs, nb), dtype=torch.int32, device=dev)
@@ -765,6 +788,7 @@ class Connectivity:
                 result[name] = t.reshape(kept + tuple(t.shape[1:])).numpy()
             return result
         for name, t in res.items():
+            t = res_packed.get(name, t)
             if t.shape[1] != fnn:
                 t = t[:, :fnn]
             tail = tuple(t.shape[1:])
@@ -1309,6 +1333,22 @@ def pinned_empty(shape, dtype=np.float32):
     across calls so that a pipeline does not allocate and page-lock its result buffers per call."""
     t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
     return t.numpy()
+
+
+def unpack_upper(packed, n_signals):
+    """Full symmetric array (..., S, S) from the packed upper triangles (..., S (S + 1) / 2) that
+    ``Connectivity.compute(packed=...)`` returns (NumPy array or torch tensor)."""
+    i, j = np.triu_indices(n_signals)
+    if isinstance(packed, torch.Tensor):
+        full = torch.empty(tuple(packed.shape[:-1]) + (n_signals, n_signals), dtype=packed.dtype, device=packed.device)
+        ti, tj = torch.from_numpy(i).to(packed.device), torch.from_numpy(j).to(packed.device)
+        full[..., ti, tj] = packed
+        full[..., tj, ti] = packed
+        return full
+    full = np.empty(tuple(packed.shape[:-1]) + (n_signals, n_signals), dtype=packed.dtype)
+    full[..., i, j] = packed
+    full[..., j, i] = packed
+    return full
 
 
 def all_pairs(n_signals):

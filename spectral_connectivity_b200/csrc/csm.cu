@@ -423,3 +423,27 @@ extern "C" int sc_power_from_csm(const void* csm_c64, int64_t BF, int64_t S, flo
     SC_LAUNCH_OK();
     return SC_OK;
 }
+
+// Upper triangle (diagonal included) of a SYMMETRIC real measure, row-major packed: element (i, j >= i) of matrix bf goes
+// to out[bf * S (S + 1) / 2 + i S - i (i - 1) / 2 + (j - i)].  Halves the device -> host bytes of coherence-type results
+// (the end-to-end step of the headline workload is bound by the host link, not by the kernels).  One CTA per matrix
+// walks the rows; thread t copies column i + t of row i, so reads and writes are both contiguous.
+__global__ void pack_upper_kernel(const float* __restrict__ in, long long BF, int S, float* __restrict__ out) {
+    const long long tri = (long long)S * (S + 1) / 2;
+    for (long long bf = blockIdx.x; bf < BF; bf += gridDim.x) {
+        const float* m = in + bf * S * S;
+        float* o = out + bf * tri;
+        for (int i = 0; i < S; ++i) {
+            const long long off = (long long)i * S - (long long)i * (i - 1) / 2 - i;  // + j
+            for (int j = i + threadIdx.x; j < S; j += blockDim.x) o[off + j] = __ldcs(&m[(long long)i * S + j]);
+        }
+    }
+}
+
+extern "C" int sc_pack_upper(const float* in, int64_t BF, int64_t S, float* out, void* stream) {
+    SC_CHECK_ARG(in && out && BF > 0 && S > 0 && S < (1 << 15), "sc_pack_upper: bad argument");
+    const long long grid = BF < 148LL * 16 ? BF : 148LL * 16;
+    pack_upper_kernel<<<(unsigned)grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, BF, (int)S, out);
+    SC_LAUNCH_OK();
+    return SC_OK;
+}

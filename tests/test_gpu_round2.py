@@ -242,3 +242,36 @@ def test_granger_grouped_problem_order_is_bit_identical(sc, n_sig, n, fs, monkey
     assert np.array_equal(c.last_granger_iterations.cpu().numpy(), it_ref)
     assert c.last_granger_executed.tolist() == ex_ref
     assert np.isfinite(got[..., 0, 1]).all() and np.isnan(got[..., 0, 0]).all()
+
+
+@pytest.mark.parametrize("output", ["numpy", "torch"])
+def test_packed_symmetric_results(sc, output):
+    """compute(packed=...): the packed upper triangle of a symmetric measure is bit-identical to the upper triangle of
+    the full result (diagonal NaNs included), through pinned out= buffers too; asymmetric measures are refused."""
+    n_sig = 37
+    x = O.synthetic_series(900, 5, n_sig, 300.0, seed=12)
+    kw = dict(sampling_frequency=300.0, time_halfbandwidth_product=3, time_window_duration=1.0)
+    c = sc.Connectivity.from_multitaper(sc.Multitaper(x, **kw), output=output, max_chunk_bytes=1)
+    names = ["coherence_magnitude", "debiased_squared_weighted_phase_lag_index", "weighted_phase_lag_index"]
+    full = c.compute(names)
+    out = None
+    if output == "numpy":
+        tri = n_sig * (n_sig + 1) // 2
+        out = {"coherence_magnitude": sc.pinned_empty(full["coherence_magnitude"].shape[:-2] + (tri,))}
+    got = c.compute(names, packed=names[:2], out=out)
+    for name in names[:2]:
+        ref = full[name] if output == "numpy" else full[name].cpu().numpy()
+        un = sc.unpack_upper(got[name], n_sig)
+        un = un if output == "numpy" else un.cpu().numpy()
+        assert got[name].shape[-1] == n_sig * (n_sig + 1) // 2 and un.shape == ref.shape
+        iu = np.triu_indices(n_sig)
+        assert np.array_equal(un[..., iu[0], iu[1]], ref[..., iu[0], iu[1]], equal_nan=True), name   # bit for bit
+        # the full result's two halves are computed independently (last-bit differences inside diagonal tiles)
+        assert_parity(np.nan_to_num(un), np.nan_to_num(ref), 1e-6, f"packed {name} vs full")
+    a, b = got[names[2]], full[names[2]]
+    assert np.array_equal(a if output == "numpy" else a.cpu().numpy(), b if output == "numpy" else b.cpu().numpy(),
+                          equal_nan=True)
+    if output == "numpy":
+        assert got["coherence_magnitude"].ctypes.data == out["coherence_magnitude"].ctypes.data
+    with pytest.raises(ValueError):
+        c.compute(names, packed=["weighted_phase_lag_index"])
