@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 NCU="ncu --clock-control none"
 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file gpurun_out/${PFX:-r02}_launches_cfg4.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${PFX:-r02}_launches_bench.log 2>&1
-for k in mt_fft_kernel csm_tc_kernel power_from_csm_kernel coherence_epilogue_vec_kernel granger_herm_kernel; do
+for k in mt_fft_kernel csm_tc_ta_kernel power_from_csm_kernel coherence_epilogue_vec_kernel granger_herm_kernel; do
     $NCU --set full --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/${PFX:-r02}_$k \
         python bench.py --workload cfg4w8 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${PFX:-r02}_ncu_$k.log 2>&1
 done
