@@ -221,3 +221,43 @@ def test_delay_group_delay_host_half_matches_reference():
     for got, key in [(d1, "delay_band"), (d2, "delay_res"), (gd[0], "gd_delay"), (gd[1], "gd_slope"), (gd[2], "gd_r")]:
         assert got.shape == g[key].shape and np.array_equal(np.isnan(got), np.isnan(g[key])), key
         assert_parity(np.nan_to_num(got), np.nan_to_num(g[key]), 1e-5, key)
+
+
+def test_granger_group_enumeration_model():
+    """Integer model of the grouped problem order of granger_herm_kernel (groups = (row i, four aligned columns), members
+    j > i): the closed-form prefix count, the binary-search decode and the member ranges cover every pair (i < j) of
+    combinations(range(S), 2) exactly once, and the pair index formula matches the lexicographic order -- for every
+    S % 4 == 0 the kernel accepts up to 1024 (csrc/granger_herm.cu: groups_before / decode in begin_group)."""
+    from itertools import combinations
+
+    def groups_before(i, s4):
+        q4, r4 = i >> 2, i & 3
+        return i * s4 - (2 * q4 * (q4 - 1) + q4 * (r4 + 1))
+
+    for S in list(range(8, 132, 4)) + [256, 512, 1024]:
+        s4 = S // 4
+        per_window = groups_before(S - 1, s4)
+        assert per_window == sum(s4 - (r + 1) // 4 for r in range(S - 1))
+        order = {p: k for k, p in enumerate(combinations(range(S), 2))} if S <= 128 else None
+        seen = 0
+        starts = [groups_before(i, s4) for i in range(S)]
+        assert all(b > a for a, b in zip(starts[:-1], starts[1:]))          # strictly increasing: the search is exact
+        for g in ([*range(per_window)] if S <= 128 else [0, 1, per_window // 2, per_window - 2, per_window - 1]):
+            lo, hi = 0, S - 2
+            while lo < hi:
+                mid = (lo + hi + 1) >> 1
+                if groups_before(mid, s4) <= g:
+                    lo = mid
+                else:
+                    hi = mid - 1
+            i = lo
+            j0 = 4 * ((i + 1) // 4 + (g - groups_before(i, s4)))
+            jlo = j0 if j0 > i else i + 1
+            assert 0 <= i < S - 1 and j0 % 4 == 0 and i < jlo <= j0 + 3 < S
+            for j in range(jlo, j0 + 4):
+                pk = i * (2 * S - i - 1) // 2 + (j - i - 1)
+                if order is not None:
+                    assert order[(i, j)] == pk
+                seen += 1
+        if S <= 128:
+            assert seen == S * (S - 1) // 2
