@@ -161,6 +161,8 @@ int sc_wilson2(const void* csm_c128, int64_t B, int nfft, double tolerance, int 
  *  F        nfft (two-sided spectrum) or nfft/2+1 with hermitian_half=1 (real time series:
  *           S(-f) = conj S(f), the from_multitaper path)
  *  pairs    int32 [n_pairs][2] or NULL for all i<j (then n_pairs is ignored)
+ *           (all pairs with S % 4 == 0 and 16-byte aligned csm / power / out_gc take the grouped problem order: one
+ *           staging pass per (window, row, 4 columns) instead of strided gathers per pair; results are identical)
  *  out_gc   f32 [B][nfft/2+1][S][S]; entries of processed pairs are overwritten ([i][j] =
  *           influence j -> i); the caller pre-fills the rest (NaN, connectivity.py:2310, 2336-2338)
  *  tail_extrapolation  0: run the reference iteration verbatim.  1 (hermitian_half only): once the

@@ -750,21 +750,28 @@ class Connectivity:
                                                      st), "sc_pack_upper")
                 offload(name, b0, b1)
             if want_granger:
-                it_c = torch.zeros((n_pairs, nb), dtype=torch.int32, device=dev)
-                fl_c = torch.zeros((n_pairs, nb), dtype=torch.int32, device=dev)
-                dst = res["pairwise_spectral_granger_prediction"][b0:b1]
-                with _lib.timed("granger"):
-                    rc = lib.sc_granger_pairwise(_lib.ptr(csm), _lib.ptr(power), nb, n_freq, nfft,
-                                                 1 if self._hermitian else 0, n_sig, _lib.ptr(pair_t), n_pairs,
-                                                 float(tolerance), int(max_iterations), 1 if tail_extrapolation else 0,
-                                                 1 if mixed_precision else 0, _lib.ptr(tw128), _lib.ptr(tw64),
-                                                 _lib.ptr(dst),
-                                                 _lib.ptr(it_c), _lib.ptr(fl_c), _lib.ptr(exec_cnt), _lib.ptr(gr_ws),
-                                                 ws_bytes, st)
-                    _lib.check(rc, "sc_granger_pairwise")
-                it_all[:, b0:b1] = it_c
-                fl_all[:, b0:b1] = fl_c
-                offload("pairwise_spectral_granger_prediction", b0, b1)
+                # With host output the chunk's windows go through the Wilson kernel in sub-launches of a few windows,
+                # each followed by its device->host copy: the Granger results are half of the bytes that leave the
+                # device and would otherwise all become available at the very end of the chunk (the copy stream idles,
+                # then lags: 18 ms of copies were still queued after the last kernel of a config-4 pass).
+                sub = nb if copy_stream is None else max(1, min(nb, self._GRANGER_SUB_WINDOWS))
+                for k0 in range(0, nb, sub):
+                    k1 = min(nb, k0 + sub)
+                    it_c = torch.zeros((n_pairs, k1 - k0), dtype=torch.int32, device=dev)
+                    fl_c = torch.zeros((n_pairs, k1 - k0), dtype=torch.int32, device=dev)
+                    dst = res["pairwise_spectral_granger_prediction"][b0 + k0:b0 + k1]
+                    with _lib.timed("granger"):
+                        rc = lib.sc_granger_pairwise(_lib.ptr(csm[k0:k1]), _lib.ptr(power[k0:k1]), k1 - k0, n_freq, nfft,
+                                                     1 if self._hermitian else 0, n_sig, _lib.ptr(pair_t), n_pairs,
+                                                     float(tolerance), int(max_iterations),
+                                                     1 if tail_extrapolation else 0, 1 if mixed_precision else 0,
+                                                     _lib.ptr(tw128), _lib.ptr(tw64), _lib.ptr(dst),
+                                                     _lib.ptr(it_c), _lib.ptr(fl_c), _lib.ptr(exec_cnt), _lib.ptr(gr_ws),
+                                                     ws_bytes, st)
+                        _lib.check(rc, "sc_granger_pairwise")
+                    it_all[:, b0 + k0:b0 + k1] = it_c
+                    fl_all[:, b0 + k0:b0 + k1] = fl_c
+                    offload("pairwise_spectral_granger_prediction", b0 + k0, b0 + k1)
             del item, csm, power, plv, pli
 
         if want_granger:
@@ -911,6 +918,7 @@ class Connectivity:
         raise NotImplementedError  # connectivity.py:1221-1224
 
     # ---- MVAR family from the full-matrix Wilson factor ----------
+    _GRANGER_SUB_WINDOWS = 3   # host output: windows per Wilson sub-launch of a chunk (see compute)
     _MVAR_MAX_SIGNALS = 1024
     _MVAR_CACHE_BYTES = 48 << 30  # above this the factor is not cached: measures stream over window chunks
 

@@ -1010,7 +1010,9 @@ int herm_launch(W2Params& p, cudaStream_t st) {
     if (p.tw32 && p.mixed) {
         // all pairs of a signal count that keeps the 16-byte row segments aligned -> grouped problem order
         const char* ng = getenv("SC_GRANGER_NO_GROUPS");
-        if (!p.pairs && p.S % 4 == 0 && p.S >= 8 && p.n_pairs == p.S * (p.S - 1) / 2 && !(ng && ng[0] == '1'))
+        const bool aligned = ((reinterpret_cast<uintptr_t>(p.csm) | reinterpret_cast<uintptr_t>(p.power) |
+                               reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;   // 16-byte row segments
+        if (!p.pairs && p.S % 4 == 0 && p.S >= 8 && p.n_pairs == p.S * (p.S - 1) / 2 && aligned && !(ng && ng[0] == '1'))
             return herm_launch_as<FPT, FFT, false, true, true>(p, st);
         return herm_launch_as<FPT, FFT, false, true>(p, st);
     }

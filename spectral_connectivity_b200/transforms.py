@@ -183,9 +183,15 @@ class Multitaper:
         copy_stream = _lib.side_stream(dev, "h2d")
         copy_stream.wait_stream(torch.cuda.current_stream(dev))
         rows = max(1, -(-n_rows // n_slabs))
+        # the first slabs grow geometrically (1/16 of a regular slab, doubling): the first window chunk of a streamed
+        # pass then waits ~1 ms for its samples instead of a whole regular slab (4.9 ms at config 4)
+        bounds, r0, size = [], 0, max(1, rows // 16)
+        while r0 < n_rows:
+            r1 = min(n_rows, r0 + size)
+            bounds.append((r0, r1))
+            r0, size = r1, min(rows, 2 * size)
         with torch.cuda.stream(copy_stream):
-            for r0 in range(0, n_rows, rows):
-                r1 = min(n_rows, r0 + rows)
+            for r0, r1 in bounds:
                 dst = self.time_series[r0:r1]
                 if ts.dtype == torch.float32:
                     dst.copy_(ts[r0:r1], non_blocking=True)
