@@ -156,10 +156,12 @@ __device__ __forceinline__ float log_ratio(double total, double part) {
     if (rest == 0.0) rest = kEps64;
     // the differences are formed in fp64; the quotients are taken in fp32 (the output is float32 and a
     // correctly rounded fp32 division of two fp32-rounded operands is accurate to 2e-7 relative)
-    const float ftotal = (float)total;
-    const float ratio = (float)rest / ftotal;
+    // one MUFU reciprocal (1 ulp) instead of two IEEE divisions: 1e-7 relative on a float32 result
+    float itotal;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(itotal) : "f"((float)total));
+    const float ratio = (float)rest * itotal;
     float gc;
-    if (ratio >= 0.5f) gc = -log1pf((float)(rest - total) / ftotal);  // = -log1p(-(total - rest)/total)
+    if (ratio >= 0.5f) gc = -log1pf((float)(rest - total) * itotal);  // = -log1p(-(total - rest)/total)
     else gc = -logf(ratio);
     return gc > 0.f ? gc : __int_as_float(0x7fc00000);
 }
@@ -697,7 +699,9 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
         // ---- Cholesky of the real lag-0 covariance, G0 = L^T (mpd.py:75-77) ----
         const double inv_nd = 1.0 / (double)N;
         const double a00 = a[0] * inv_nd, a10 = a[1] * inv_nd, a11 = a[2] * inv_nd;
-        const double l00 = sqrt(a00), l10 = a10 / l00, d11 = a11 - l10 * l10, l11 = sqrt(d11);
+        // reciprocal square roots (one MUFU + Newton each) instead of sqrt, division, sqrt
+        const double x00 = rsqrt(a00);
+        const double l00 = a00 * x00, l10 = a10 * x00, d11 = a11 - l10 * l10, l11 = d11 * rsqrt(d11);
         int flag = 0, it_done = 0;
         if (!(a00 > 0.0) || !(d11 > 0.0) || !isfinite(l00) || !isfinite(l11)) flag = SC_FLAG_NOT_SPD;
         constexpr int GN = LEAN ? 1 : FPT;  // LEAN keeps the fp64 factor in shared memory (G64)
@@ -925,8 +929,10 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
         const double imdet = 1.0 / mdet;
         const double v00 = m11 * imdet, v01 = -h01 * imdet, v10 = -h10 * imdet, v11 = m00 * imdet;
         const double c00 = h00 * h00 + h01 * h01, c01 = h00 * h10 + h01 * h11, c11 = h10 * h10 + h11 * h11;
-        const double r01 = c11 - c01 * c01 / c00;
-        const double r10 = c00 - c01 * c01 / c11;
+        // r01 = c11 - c01^2 / c00 and r10 = c00 - c01^2 / c11 share the numerator det(Sigma): one division
+        const double sdet = c00 * c11 - c01 * c01, icc = 1.0 / (c00 * c11);
+        const double r01 = sdet * c11 * icc;
+        const double r10 = sdet * c00 * icc;
 #pragma unroll
         for (int q = 0; q < FPT; ++q) {
             const int f = threadIdx.x + q * kThreads;
