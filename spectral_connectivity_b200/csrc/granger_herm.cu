@@ -66,6 +66,7 @@ template <typename PLAN> struct PlanR0 { static constexpr int value = 0; };
 template <int N, int R0, int... REST> struct PlanR0<ScStaticPlan<N, R0, REST...>> { static constexpr int value = R0; };
 
 struct DynFft {
+    static constexpr int kStaticN = 0;  // FFT length known at run time only
     static constexpr bool kRegTw = false;
     typedef NoTwRegs TwRegs;
     static __device__ __forceinline__ void load_regs(TwRegs&, const cx<float>*) {}
@@ -110,6 +111,7 @@ template <typename PLAN> struct StatFftRegs<PLAN, true> {
 };
 
 template <typename PLAN> struct StatFft : StatFftRegs<PLAN> {
+    static constexpr int kStaticN = PLAN::n;  // compile-time length: bin guards, mirror indices and 1/N fold to constants
     static constexpr bool kPrefetch = true;  // fetch the next problem's spectrum under the epilogue
     static constexpr int kCut = (PLAN::n + 1) / 2;  // the plus operator keeps lags [0, kCut)
     template <typename R> struct Fused {
@@ -229,12 +231,10 @@ __device__ __forceinline__ void herm_iteration(cx<R> (&g00)[FPT], cx<R> (&g01)[F
             const int fm = f == 0 ? 0 : N - f;
             ZA[f] = cmake<R>(b00, b11);
             ZA[fm] = cmake<R>(b00, b11);
-            if (f == fm) {
-                ZA[N + f] = cmake<R>(b01.x, b01.x);  // DC / Nyquist: B01 is real
-            } else {
-                ZA[N + f] = cmake<R>(b01.x + b01.y, b01.x + b01.y);
-                ZA[N + fm] = cmake<R>(b01.x - b01.y, b01.x - b01.y);
-            }
+            // DC / Nyquist (f == fm): B01 is real there -- every operand of its imaginary part is an exact zero -- so
+            // the two stores write the same value and no branch is needed
+            ZA[N + f] = cmake<R>(b01.x + b01.y, b01.x + b01.y);
+            ZA[N + fm] = cmake<R>(b01.x - b01.y, b01.x - b01.y);
         }
     }
     __syncthreads();
@@ -399,12 +399,8 @@ __device__ __forceinline__ void herm_iteration_defect(const GACC gacc,
             const int fm = f == 0 ? 0 : N - f;
             ZA[f] = cmake<float>(e00, e11);
             ZA[fm] = cmake<float>(e00, e11);
-            if (f == fm) {
-                ZA[N + f] = cmake<float>(e01x, e01x);
-            } else {
-                ZA[N + f] = cmake<float>(e01x + e01y, e01x + e01y);
-                ZA[N + fm] = cmake<float>(e01x - e01y, e01x - e01y);
-            }
+            ZA[N + f] = cmake<float>(e01x + e01y, e01x + e01y);   // f == fm: e01y is an exact zero (see herm_iteration)
+            ZA[N + fm] = cmake<float>(e01x - e01y, e01x - e01y);
         }
     }
     __syncthreads();
@@ -513,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
     __shared__ unsigned redf[2 * kWarps];
     __shared__ unsigned long long redd[2 * 6 * kWarps];
     int phase_f = 0, phase_d = 0;
-    const int N = p.nfft;
+    const int N = FFT::kStaticN > 0 ? FFT::kStaticN : p.nfft;
     const int fnn = N / 2 + 1;
     __shared__ double lag0_sh[3];
     __shared__ float lag0f_sh[3];
@@ -753,8 +749,8 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
                     herm_iteration<float, FPT, FFT, kRT>(f00, f01, f10, f11, s00, s11, s01, 1.f, 1.f, 1.f, ZAf,
                                                          ZBf, p.plan, twsf, N, fnn, lag0f_sh, stf, &twr);
                     // update minus its constant-matrix (tail) part; the barrier inside also fences the buffers
-                    const float errf = sqrtf(block_max_nonneg(stf[1], redf, phase_f));
-                    if (errf < kSwitch) {
+                    const float errf2 = block_max_nonneg(stf[1], redf, phase_f);  // squared: compared with kSwitch^2
+                    if (errf2 < kSwitch * kSwitch) {
                         ++it0;
                         break;
                     }
@@ -785,11 +781,11 @@ __global__ void __launch_bounds__(kThreads, 512 / kThreads) granger_herm_kernel(
                                                          N, fnn, lag0_sh, st);
                 }
                 block_maxn_nonneg<6>(st, redd, phase_d);  // also fences ZA/ZB reuse
-                const double err = sqrt(st[0]);
+                const double tol2 = p.tol * p.tol;  // the maxima are squared magnitudes: compare squares, no sqrt
                 it_done = it + 1;
                 ++cnt_f64;
-                converged = err < p.tol;
-                if (!converged && p.tail && sqrt(st[1]) < kTailRest * p.tol) {
+                converged = st[0] < tol2;
+                if (!converged && p.tail && st[1] < kTailRest * kTailRest * tol2) {
                     // Tail in closed form.  The reference halves every lag-0 coefficient of the causal factor
                     // and THEN zeroes its lower triangle (mpd.py:132-138), so the lag-0 off-diagonal residual
                     // is only half-corrected per iteration: once every other mode has converged (the update
