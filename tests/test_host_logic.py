@@ -261,3 +261,18 @@ def test_granger_group_enumeration_model():
                 seen += 1
         if S <= 128:
             assert seen == S * (S - 1) // 2
+
+
+def test_unpack_upper_numpy_roundtrip():
+    """unpack_upper (host side of compute(packed=...)): the packed index of (i, j >= i) is i S - i (i - 1) / 2 + j - i,
+    the order sc_pack_upper writes (csrc/csm.cu) and numpy.triu_indices enumerates."""
+    from spectral_connectivity_b200.connectivity import unpack_upper
+    rng = np.random.default_rng(0)
+    for n_sig in (1, 2, 5, 37):
+        full = rng.normal(size=(2, 3, n_sig, n_sig)).astype(np.float32)
+        full = full + np.swapaxes(full, -1, -2)
+        packed = np.stack([[full[a, b][np.triu_indices(n_sig)] for b in range(3)] for a in range(2)])
+        for i in range(n_sig):
+            for j in range(i, n_sig):
+                assert packed[0, 0, i * n_sig - i * (i - 1) // 2 + j - i] == full[0, 0, i, j]
+        assert np.array_equal(unpack_upper(packed, n_sig), full)

@@ -11,6 +11,8 @@ x_host = torch.empty(x_dev.shape, dtype=torch.float32, pin_memory=True); x_host.
 x_np = x_host.numpy()
 kw = dict(sampling_frequency=wl['fs'], time_halfbandwidth_product=wl['NW'], time_window_duration=wl['duration'])
 bufs = None
+if len(sys.argv) > 1:
+    sc.Connectivity._GRANGER_SUB_WINDOWS = int(sys.argv[1])
 for i in range(8):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
