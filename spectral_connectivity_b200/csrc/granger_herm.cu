@@ -15,6 +15,14 @@
 //    inverse+forward pair instead of 7;
 //  * the Granger epilogue (transfer function, noise covariance, log ratio) is evaluated from the
 //    registers and written straight into the (B, Fnn, S, S) output.
+//
+// Kernel variants (template flags of granger_herm_kernel; the launcher herm_launch picks one):
+//   <.., LEAN=0, MIXED=0>           runtime precision mode, fp64 + fp32 buffers (88 KB at nfft = 1000): plain fp64 calls
+//   <.., LEAN=0, MIXED=1>           mixed precision known at launch: fp32 buffers only (40 KB), explicit pair subsets
+//   <.., LEAN=0, MIXED=1, GROUPED=1> the headline path: all pairs, S % 4 == 0 -- problems ordered by (window, row, four
+//                                   aligned columns), one staging pass per group, 16-byte row stores (84 KB)
+//   <.., LEAN=1>                    experiment (SC_GRANGER_LEAN=1): fp64 factor in shared memory, register twiddles
+// Measured history and dead ends: profiles/r02_granger_experiments.txt.
 #include <stdlib.h>
 
 #include "wilson_common.cuh"
@@ -27,12 +35,12 @@ constexpr int kMaxF32Iters = 12;     // fp32 phase never runs longer than this
 #ifndef SC_GRANGER_GROUP
 #define SC_GRANGER_GROUP 4
 #endif
-constexpr int kGroup = SC_GRANGER_GROUP;  // consecutive pair indices one CTA handles back to back (sector reuse in L1)
+constexpr int kGroup = SC_GRANGER_GROUP;  // non-grouped order: consecutive pair indices one CTA handles back to back
 #ifndef SC_TAIL_JUMP_PA
 // closed-form late tail once the diagonal steps of the tail recursion are below these (float64 model of both forms:
 // tests/test_granger_tail_model.py -- same stopping iterate in 4000 of 4000 random problems, accumulated factor equal
-// to 5e-10 at 1e-6 / 1e-9 and to 1.5e-11 at 1e-7 / 1e-10; measured 263.3 ms without the jump region widened to 1e-9,
-// 260.1 ms at 1e-7)
+// to 5e-10 at 1e-6 / 1e-9 and to 1.5e-11 at 1e-7 / 1e-10; measured: 267.2 ms without the closed form, 263.3 ms at
+// 1e-9 / 1e-12, 260.1 ms at 1e-7 / 1e-10)
 #define SC_TAIL_JUMP_PA 1e-6
 #define SC_TAIL_JUMP_PD 1e-9
 #endif
