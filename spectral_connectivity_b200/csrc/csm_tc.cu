@@ -24,6 +24,10 @@
 //               (the tensor core accumulates round-toward-zero), finally scale, store C and conj(C)^T
 // Pipelines: smem ring (full_raw -> full_cvt -> empty) and TMEM ring (tmem_full/tmem_empty), all
 // mbarriers.  Every spin is bounded and traps, so a protocol bug cannot hang the device.
+//
+// TWO kernels live here: csm_tc_kernel (both operands from shared memory, the round-1 design described above, kept behind
+// SC_CSM_TA=0) and csm_tc_ta_kernel (DEFAULT: the row-block operand comes from tensor memory, see its own header below).
+// Both issue their MMAs from a warp-uniform loop with the instruction predicated on the elected lane.
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
