@@ -747,6 +747,8 @@ def run_gpu(args, wl_name, wl, shard, ctx):
                                   "link, whatever the GPUs do",
                 **({} if e2e_ok else {"error": e2e_error or "another rank failed to stage its host buffers"})},
         "e2e_packed": e2e_packed,
+        # the same throughput counted in UNIQUE pairs, W Fnn S (S - 1) / 2 per recording
+        "value_unique_pairs": value * (wl["S"] - 1) / (2.0 * wl["S"]),
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "stages": stage_rows, "sanity": sanity,
         "simt_peaks_tflops": simt,
     }
